@@ -1,0 +1,358 @@
+// C ABI of liblogmel_b200.so (declared in include/logmel.h).
+//
+// Build (see __graft_entry__.build / Makefile):
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC \
+//        -shared -o liblogmel_b200.so logmel_api.cu
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/logmel.h"
+#include "logmel_kernel.cuh"
+#include "logmel_tables.h"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(expr)                                  \
+  do {                                                  \
+    cudaError_t e__ = (expr);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+  } while (0)
+
+constexpr int kMaxGroup = 64;
+
+struct HostPipe {   // staging for lm_forward_host
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+  float* d_wave[2] = {};
+  float* d_out[2] = {};
+  int* d_len[2] = {};
+  void* d_scratch[2] = {};
+  size_t wave_cap = 0, out_cap = 0, len_cap = 0, scratch_cap = 0;
+  bool ready = false;
+};
+
+}  // namespace
+
+struct lm_handle {
+  lm_config cfg{};
+  int n_sm = 0, ctas_per_sm = 0, smem = 0, threads = 0, frames_per_tile = 0;
+  std::mutex host_mu;
+  HostPipe pipe;
+  virtual ~lm_handle() {}
+  virtual int launch(const lm::KArgs& a, int grid, cudaStream_t st) = 0;
+};
+
+namespace {
+
+template <class G>
+struct Impl : lm_handle {
+  lm::Tables<G> tab;
+  int launch(const lm::KArgs& a, int grid, cudaStream_t st) override {
+    void* args[] = {(void*)&tab, (void*)&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)lm::logmel_kernel<G>, dim3(grid), dim3(G::THREADS),
+                                                args, lm::Lay<G>::BYTES, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(logmel_kernel)");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+};
+
+template <class G>
+int make(lm_handle** out, const lm_config* cfg, const float* window) {
+  auto h = std::make_unique<Impl<G>>();
+  h->cfg = *cfg;
+  h->cfg.fbank = nullptr;
+  h->cfg.window = nullptr;
+  std::string err = lm::build_tables<G>(h->tab, window, cfg->fbank, cfg->n_mels);
+  if (!err.empty()) return fail(LM_ERR_FBANK, "%s", err.c_str());
+  const int smem = (int)lm::Lay<G>::BYTES;
+  CUDA_TRY(cudaFuncSetAttribute(lm::logmel_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lm::logmel_kernel<G>, G::THREADS, smem));
+  if (occ < 1) return fail(LM_ERR_NO_DEVICE, "forward kernel does not fit on this device (smem %d B)", smem);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (!prop.cooperativeLaunch) return fail(LM_ERR_NO_DEVICE, "device lacks cooperative launch");
+  h->n_sm = prop.multiProcessorCount;
+  h->ctas_per_sm = occ;
+  h->smem = smem;
+  h->threads = G::THREADS;
+  h->frames_per_tile = G::F;
+  *out = h.release();
+  return 0;
+}
+
+int64_t frames_for(const lm_config& c, int64_t n_samples) {
+  return 1 + n_samples / c.hop - (c.drop_last ? 1 : 0);
+}
+
+void choose_grid(const lm_handle* h, int64_t batch, int tiles, int* group, int* n_groups) {
+  const int total = h->n_sm * h->ctas_per_sm;
+  // steady state: ~n_sm/4 clips in flight keeps the un-normalised slabs L2 resident;
+  // small batches: spread every clip over as many CTAs as it has tiles
+  const int steady_groups = std::max(1, h->n_sm / 4);
+  int g = std::max(1, total / steady_groups);
+  if (batch < steady_groups) g = (int)std::min<int64_t>(kMaxGroup, std::max<int64_t>(g, total / std::max<int64_t>(batch, 1)));
+  g = std::max(1, std::min(std::min(g, kMaxGroup), tiles));
+  int ng = std::max(1, total / g);
+  if ((int64_t)ng > batch) ng = (int)batch;
+  *group = g;
+  *n_groups = ng;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lm_version(void) { return LM_ABI_VERSION; }
+const char* lm_last_error(void) { return g_err.c_str(); }
+int64_t lm_launch_count(void) { return g_launches.load(); }
+
+int lm_create(lm_handle** out, const lm_config* cfg) {
+  if (!out || !cfg || !cfg->fbank) return fail(LM_ERR_NULL, "lm_create: out, cfg and cfg->fbank must be non-NULL");
+  *out = nullptr;
+  if (cfg->log_mode < LM_LOG_NONE || cfg->log_mode > LM_LOG10_CLAMP) return fail(LM_ERR_MODE, "unknown log_mode %d", cfg->log_mode);
+  if (cfg->n_mels < 1 || cfg->n_mels > lm::kMaxMels) return fail(LM_ERR_FBANK, "n_mels=%d not in [1,%d]", cfg->n_mels, lm::kMaxMels);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(LM_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(LM_ERR_NO_DEVICE, "device %d out of range", cfg->device);
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  std::vector<float> win;
+  if (cfg->window) win.assign(cfg->window, cfg->window + cfg->n_fft);
+  else if (cfg->n_fft > 0) win = lm::hann_periodic(cfg->n_fft);
+  const int v = cfg->variant;
+  if (cfg->n_fft == 400 && cfg->hop == 160) {
+    if (v == 1) return make<lm::Geo<400, 160, 1>>(out, cfg, win.data());
+    return make<lm::Geo<400, 160, 2>>(out, cfg, win.data());
+  }
+  if (cfg->n_fft == 1024 && cfg->hop == 512) return make<lm::Geo<1024, 512, 1>>(out, cfg, win.data());
+  if (cfg->n_fft == 1024 && cfg->hop == 128) return make<lm::Geo<1024, 128, 1>>(out, cfg, win.data());
+  return fail(LM_ERR_GEOMETRY, "no kernel for n_fft=%d hop=%d (supported: 400/160, 1024/512, 1024/128)", cfg->n_fft, cfg->hop);
+}
+
+void lm_destroy(lm_handle* h) {
+  if (!h) return;
+  HostPipe& p = h->pipe;
+  if (p.ready) {
+    cudaSetDevice(h->cfg.device);
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(p.d_wave[i]);
+      cudaFree(p.d_out[i]);
+      cudaFree(p.d_len[i]);
+      cudaFree(p.d_scratch[i]);
+      cudaEventDestroy(p.ev_h2d[i]);
+      cudaEventDestroy(p.ev_comp[i]);
+      cudaEventDestroy(p.ev_d2h[i]);
+    }
+    cudaStreamDestroy(p.s_h2d);
+    cudaStreamDestroy(p.s_comp);
+    cudaStreamDestroy(p.s_d2h);
+  }
+  delete h;
+}
+
+int64_t lm_num_frames(const lm_handle* h, int64_t n_samples) {
+  if (!h) return LM_ERR_NULL;
+  return frames_for(h->cfg, n_samples);
+}
+
+size_t lm_scratch_bytes(const lm_handle* h, int64_t batch) {
+  if (!h || batch < 0) return 0;
+  return (size_t)batch * (kMaxGroup + 1) * 4 + 16;
+}
+
+int lm_kernel_info(const lm_handle* h, int32_t* n_sm, int32_t* ctas_per_sm, int32_t* smem_bytes,
+                   int32_t* threads, int32_t* frames_per_tile) {
+  if (!h) return fail(LM_ERR_NULL, "lm_kernel_info: NULL handle");
+  if (n_sm) *n_sm = h->n_sm;
+  if (ctas_per_sm) *ctas_per_sm = h->ctas_per_sm;
+  if (smem_bytes) *smem_bytes = h->smem;
+  if (threads) *threads = h->threads;
+  if (frames_per_tile) *frames_per_tile = h->frames_per_tile;
+  return 0;
+}
+
+int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_stride, int64_t n_samples,
+               const int32_t* d_lengths, float* d_out, float* d_clip_max, void* d_scratch,
+               size_t scratch_bytes, void* stream) {
+  if (!h) return fail(LM_ERR_NULL, "lm_forward: NULL handle");
+  if (batch == 0) return 0;
+  if (!d_wave || !d_out) return fail(LM_ERR_NULL, "lm_forward: d_wave and d_out must be non-NULL");
+  const lm_config& c = h->cfg;
+  if (batch < 0 || batch > (1 << 24)) return fail(LM_ERR_SHAPE, "batch=%lld out of range", (long long)batch);
+  if (n_samples <= c.n_fft / 2 || n_samples > (1LL << 30))
+    return fail(LM_ERR_SHAPE, "n_samples=%lld: reflect padding needs more than n_fft/2=%d samples (as torch.stft)",
+                (long long)n_samples, c.n_fft / 2);
+  if (clip_stride < 0 || (!d_lengths && clip_stride < n_samples))
+    return fail(LM_ERR_SHAPE, "clip_stride=%lld smaller than n_samples=%lld without d_lengths",
+                (long long)clip_stride, (long long)n_samples);
+  const int64_t n_frames = frames_for(c, n_samples);
+  if (n_frames < 1) return fail(LM_ERR_SHAPE, "n_samples=%lld gives no frame", (long long)n_samples);
+  const bool norm = c.log_mode == LM_LOG10_CLAMP_WHISPER_NORM;
+  if (norm && (!d_scratch || scratch_bytes < lm_scratch_bytes(h, batch)))
+    return fail(LM_ERR_SCRATCH, "scratch %zu B < required %zu B", scratch_bytes, lm_scratch_bytes(h, batch));
+  if (norm && ((uintptr_t)d_scratch & 15)) return fail(LM_ERR_SCRATCH, "scratch must be 16-byte aligned");
+
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = -1;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != c.device) CUDA_TRY(cudaSetDevice(c.device));
+
+  lm::KArgs a{};
+  a.wave = d_wave;
+  a.clip_stride = clip_stride;
+  a.lengths = d_lengths;
+  a.out = d_out;
+  a.clip_max = d_clip_max;
+  a.batch = (int)batch;
+  a.n_samples = (int)n_samples;
+  a.n_frames = (int)n_frames;
+  a.n_mels = c.n_mels;
+  a.log_mode = c.log_mode;
+  a.log_add = 0.0f;
+  a.log_floor = 0.0f;
+  a.log_scale = 1.0f;
+  if (c.log_mode == LM_LOG10_CLAMP_WHISPER_NORM || c.log_mode == LM_LOG10_CLAMP) {
+    a.log_floor = c.log_param;
+    a.log_scale = 0.30102999566398120f;   // log10(2)
+  } else if (c.log_mode == LM_LN_PLUS_EPS) {
+    a.log_add = c.log_param;
+    a.log_scale = 0.69314718055994531f;   // ln(2)
+  }
+  a.tiles_per_clip = (int)((n_frames + h->frames_per_tile - 1) / h->frames_per_tile);
+  choose_grid(h, batch, a.tiles_per_clip, &a.group, &a.n_groups);
+  a.vec_ok = (n_frames % 4 == 0) && (((uintptr_t)d_out & 15) == 0);
+  if (norm) {
+    a.gcnt = reinterpret_cast<int*>(d_scratch);
+    a.gmax = reinterpret_cast<float*>(d_scratch) + ((batch + 3) / 4) * 4;
+    CUDA_TRY(cudaMemsetAsync(a.gcnt, 0, (size_t)batch * sizeof(int), st));
+  }
+  int rc = h->launch(a, a.group * a.n_groups, st);
+  if (dev != c.device && dev >= 0) cudaSetDevice(dev);
+  return rc;
+}
+
+int lm_host_register(void* p, size_t bytes) {
+  if (!p) return fail(LM_ERR_NULL, "lm_host_register: NULL");
+  CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+int lm_host_unregister(void* p) {
+  if (!p) return fail(LM_ERR_NULL, "lm_host_unregister: NULL");
+  CUDA_TRY(cudaHostUnregister(p));
+  return 0;
+}
+
+int lm_forward_host(lm_handle* h, const float* h_wave, int64_t batch, int64_t clip_stride, int64_t n_samples,
+                    const int32_t* h_lengths, float* h_out) {
+  if (!h) return fail(LM_ERR_NULL, "lm_forward_host: NULL handle");
+  if (batch == 0) return 0;
+  if (!h_wave || !h_out) return fail(LM_ERR_NULL, "lm_forward_host: h_wave and h_out must be non-NULL");
+  const lm_config& c = h->cfg;
+  if (batch < 0) return fail(LM_ERR_SHAPE, "batch=%lld", (long long)batch);
+  if (n_samples <= c.n_fft / 2) return fail(LM_ERR_SHAPE, "n_samples=%lld too short for reflect padding", (long long)n_samples);
+  const int64_t n_frames = frames_for(c, n_samples);
+  if (n_frames < 1) return fail(LM_ERR_SHAPE, "n_samples=%lld gives no frame", (long long)n_samples);
+  std::lock_guard<std::mutex> lock(h->host_mu);
+  int dev = -1;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != c.device) CUDA_TRY(cudaSetDevice(c.device));
+
+  // chunking: ~64 MiB of waveform per chunk, at least 1 clip, at most the whole batch
+  const size_t clip_in = (size_t)n_samples * 4, clip_out = (size_t)c.n_mels * n_frames * 4;
+  int64_t chunk = std::max<int64_t>(1, (int64_t)((64u << 20) / clip_in));
+  chunk = std::min(chunk, batch);
+  // copy width: clips shorter than n_samples on the host are copied at their stride
+  const int64_t row = std::min(clip_stride, n_samples);
+
+  HostPipe& p = h->pipe;
+  if (!p.ready) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&p.s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p.s_comp, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p.s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaEventCreateWithFlags(&p.ev_h2d[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&p.ev_comp[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&p.ev_d2h[i], cudaEventDisableTiming));
+    }
+    p.ready = true;
+  }
+  const size_t need_w = (size_t)chunk * clip_in, need_o = (size_t)chunk * clip_out;
+  const size_t need_l = (size_t)chunk * 4, need_s = lm_scratch_bytes(h, chunk);
+  for (int i = 0; i < 2; ++i) {
+    if (p.wave_cap < need_w) { cudaFree(p.d_wave[i]); p.d_wave[i] = nullptr; CUDA_TRY(cudaMalloc(&p.d_wave[i], need_w)); }
+    if (p.out_cap < need_o) { cudaFree(p.d_out[i]); p.d_out[i] = nullptr; CUDA_TRY(cudaMalloc(&p.d_out[i], need_o)); }
+    if (p.len_cap < need_l) { cudaFree(p.d_len[i]); p.d_len[i] = nullptr; CUDA_TRY(cudaMalloc(&p.d_len[i], need_l)); }
+    if (p.scratch_cap < need_s) { cudaFree(p.d_scratch[i]); p.d_scratch[i] = nullptr; CUDA_TRY(cudaMalloc(&p.d_scratch[i], need_s)); }
+  }
+  p.wave_cap = std::max(p.wave_cap, need_w);
+  p.out_cap = std::max(p.out_cap, need_o);
+  p.len_cap = std::max(p.len_cap, need_l);
+  p.scratch_cap = std::max(p.scratch_cap, need_s);
+
+  int it = 0;
+  for (int64_t c0 = 0; c0 < batch; c0 += chunk, ++it) {
+    const int b = it & 1;
+    const int64_t nb = std::min(chunk, batch - c0);
+    // buffer b was last used by chunk it-2: its compute must be done before new input lands,
+    // and its D2H before the kernel overwrites d_out[b]
+    if (it >= 2) {
+      CUDA_TRY(cudaStreamWaitEvent(p.s_h2d, p.ev_comp[b], 0));
+      CUDA_TRY(cudaStreamWaitEvent(p.s_comp, p.ev_d2h[b], 0));
+    }
+    if (row == n_samples && clip_stride == n_samples) {
+      CUDA_TRY(cudaMemcpyAsync(p.d_wave[b], h_wave + c0 * clip_stride, (size_t)nb * clip_in, cudaMemcpyHostToDevice, p.s_h2d));
+    } else {
+      if (row < n_samples) CUDA_TRY(cudaMemsetAsync(p.d_wave[b], 0, (size_t)nb * clip_in, p.s_h2d));
+      CUDA_TRY(cudaMemcpy2DAsync(p.d_wave[b], clip_in, h_wave + c0 * clip_stride, (size_t)clip_stride * 4,
+                                 (size_t)row * 4, (size_t)nb, cudaMemcpyHostToDevice, p.s_h2d));
+    }
+    if (h_lengths)
+      CUDA_TRY(cudaMemcpyAsync(p.d_len[b], h_lengths + c0, (size_t)nb * 4, cudaMemcpyHostToDevice, p.s_h2d));
+    CUDA_TRY(cudaEventRecord(p.ev_h2d[b], p.s_h2d));
+    CUDA_TRY(cudaStreamWaitEvent(p.s_comp, p.ev_h2d[b], 0));
+    int rc = lm_forward(h, p.d_wave[b], nb, n_samples, n_samples, h_lengths ? p.d_len[b] : nullptr, p.d_out[b],
+                        nullptr, p.d_scratch[b], p.scratch_cap, p.s_comp);
+    if (rc != 0) return rc;
+    CUDA_TRY(cudaEventRecord(p.ev_comp[b], p.s_comp));
+    CUDA_TRY(cudaStreamWaitEvent(p.s_d2h, p.ev_comp[b], 0));
+    CUDA_TRY(cudaMemcpyAsync(h_out + c0 * (int64_t)c.n_mels * n_frames, p.d_out[b], (size_t)nb * clip_out,
+                             cudaMemcpyDeviceToHost, p.s_d2h));
+    CUDA_TRY(cudaEventRecord(p.ev_d2h[b], p.s_d2h));
+  }
+  CUDA_TRY(cudaStreamSynchronize(p.s_d2h));
+  CUDA_TRY(cudaStreamSynchronize(p.s_comp));
+  CUDA_TRY(cudaStreamSynchronize(p.s_h2d));
+  if (dev != c.device && dev >= 0) cudaSetDevice(dev);
+  return 0;
+}
+
+}  // extern "C"

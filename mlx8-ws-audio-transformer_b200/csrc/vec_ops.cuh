@@ -52,16 +52,8 @@ LM_D f32x2 vpack(float lo, float hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
   return r;
 }
-LM_D float vlo(f32x2 a) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
-  return lo;
-}
-LM_D float vhi(f32x2 a) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
-  return hi;
-}
+LM_D float vlo(f32x2 a) { return __uint_as_float((unsigned)(a.v & 0xffffffffull)); }
+LM_D float vhi(f32x2 a) { return __uint_as_float((unsigned)(a.v >> 32)); }
 LM_D f32x2 vadd(f32x2 a, f32x2 b) {
   f32x2 r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
