@@ -73,10 +73,18 @@ namespace {
 template <class G>
 struct Impl : lm_handle {
   lm::Tables<G> tab;
+  const void* kernel = nullptr;
+  static const void* pick(int log_mode) {
+    switch (log_mode) {
+      case LM_LOG_NONE: return (const void*)lm::logmel_kernel<G, 0>;
+      case LM_LN_PLUS_EPS: return (const void*)lm::logmel_kernel<G, 2>;
+      case LM_LOG10_CLAMP: return (const void*)lm::logmel_kernel<G, 1>;
+      default: return (const void*)lm::logmel_kernel<G, 3>;
+    }
+  }
   int launch(const lm::KArgs& a, int grid, cudaStream_t st) override {
     void* args[] = {(void*)&tab, (void*)&a};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)lm::logmel_kernel<G>, dim3(grid), dim3(G::THREADS),
-                                                args, lm::Lay<G>::BYTES, st);
+    cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(G::THREADS), args, lm::Lay<G>::BYTES, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(logmel_kernel)");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -92,9 +100,10 @@ int make(lm_handle** out, const lm_config* cfg, const float* window) {
   std::string err = lm::build_tables<G>(h->tab, window, cfg->fbank, cfg->n_mels);
   if (!err.empty()) return fail(LM_ERR_FBANK, "%s", err.c_str());
   const int smem = (int)lm::Lay<G>::BYTES;
-  CUDA_TRY(cudaFuncSetAttribute(lm::logmel_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  h->kernel = Impl<G>::pick(cfg->log_mode);
+  CUDA_TRY(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lm::logmel_kernel<G>, G::THREADS, smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->kernel, G::THREADS, smem));
   if (occ < 1) return fail(LM_ERR_NO_DEVICE, "forward kernel does not fit on this device (smem %d B)", smem);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
@@ -250,6 +259,7 @@ int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_st
   a.tiles_per_clip = (int)((n_frames + h->frames_per_tile - 1) / h->frames_per_tile);
   choose_grid(h, batch, a.tiles_per_clip, &a.group, &a.n_groups);
   a.vec_ok = (n_frames % 4 == 0) && (((uintptr_t)d_out & 15) == 0);
+  a.tma_ok = (((uintptr_t)d_wave & 15) == 0) && (clip_stride % 4 == 0);
   if (norm) {
     a.gcnt = reinterpret_cast<int*>(d_scratch);
     a.gmax = reinterpret_cast<float*>(d_scratch) + ((batch + 3) / 4) * 4;

@@ -25,7 +25,7 @@ namespace lm {
 enum : int { LOG_NONE = 0, LOG10_CLAMP_WHISPER_NORM = 1, LN_PLUS_EPS = 2, LOG10_CLAMP = 3 };
 
 constexpr int kMaxMels = 128;
-constexpr int kMaxMelWeights = 2048;
+constexpr int kMaxMelWeights = 3072;
 
 // ---------------------------------------------------------------------------------------
 // compile-time geometry
@@ -40,31 +40,48 @@ struct Geo {
   static constexpr int N1 = Split<NFFT>::N1, N2 = Split<NFFT>::N2;
   static constexpr int H1 = N1 / 2;                 // stage-2 tasks are k1 = 0..H1
   static constexpr int NBINS = N / 2 + 1;
-  static constexpr int NW = H1;                     // warps per CTA
-  static constexpr int THREADS = NW * 32;
+  static constexpr int NW = H1;                     // warps that share stage 1 (N2 / NW columns each)
+  static constexpr int NWK = NW + 1;                // + the producer warp: loads tiles, takes the
+                                                    //   k1 = H1 row of stage 2 and a run of filters
+  static constexpr int THREADS = NWK * 32;
   static constexpr int F = 32 * PK;                 // frames per tile
   static constexpr int SPAN = (F - 1) * HOP + N;    // samples a tile touches
-  static constexpr int PITCH = HOP + 1;             // odd pitch: lane stride = 1 bank
+  // Waveform rows of HOP samples, 4 pad words each: every row starts 16-byte aligned (one TMA
+  // bulk copy per row) and the row stride is 4 banks, which the stage-1 lane map (8 frames x 4
+  // adjacent columns per warp) turns into 32 distinct banks.
+  static constexpr int PITCH = HOP + 4;
   static constexpr int ROWS = (SPAN + HOP - 1) / HOP;
   static constexpr int WAVE_FLOATS = ROWS * PITCH;
   static constexpr int S1_STRIDE = N1 + 2 * H1;     // per-column constants: w[N1], (twr,twi)[1..H1]
-  // Y: k1 = 0 is real (one plane), k1 = 1..H1 complex (re, im interleaved per lane)
-  static constexpr int Y0_ELEMS = N2 * 32;               // in units of T
-  static constexpr int Y_ELEMS = Y0_ELEMS + H1 * N2 * 32 * 2;
+  // Y (units of T): one real plane [k1 = 0..H1][b][lane], then one imaginary plane
+  // [k1 = 1..H1][b][lane] (row k1 = 0 is purely real).  Separate planes let stage 1 store each
+  // 64-bit packed value straight from the register pair it was computed in.
+  static constexpr int YRE_ELEMS = (H1 + 1) * N2 * 32;
+  static constexpr int Y_ELEMS = YRE_ELEMS + H1 * N2 * 32;
   static constexpr int P_ELEMS = NBINS * 32;
   static_assert(HOP % N2 == 0, "a column must not straddle a hop row");
-  static_assert(N2 % NW == 0, "stage-1 columns must divide evenly over the warps");
+  static_assert(S1_STRIDE % 4 == 0, "stage-1 constants are fetched as float4");
+  static_assert(HOP % 32 == 0, "the row pitch must be 4 banks past a multiple of 32");
+  static constexpr int CGROUPS = N2 / 4;            // stage-1 tasks: (4 frame octets) x (N2/4 column quads)
+  static constexpr int S1_TASKS = 4 * CGROUPS;
+  static_assert(N2 % 4 == 0 && S1_TASKS % NW == 0, "stage-1 tasks must divide evenly over the warps");
 };
 
 // kernel parameters that live in the constant bank (__grid_constant__)
+//
+// Mel projection layout: warp w owns filters [mel_begin[w], mel_begin[w+1]).  Every filter of
+// that run is stored as mel_ng[w] groups of 4 consecutive-bin weights (zero padded), starting
+// at bin mel_lo[m]; its weights sit at melw[4 * (mel_woff[w] + (m - mel_begin[w]) * mel_ng[w])].
+// A fixed group count per warp keeps the inner loop free of per-filter control flow, and one
+// 128-bit constant load fetches the four weights of a group.
 template <class G>
-struct Tables {
-  float s1[G::N2 * G::S1_STRIDE];        // stage-1 constants per column b
-  float melw[kMaxMelWeights];            // banded filter weights, filter after filter
-  unsigned short mel_lo[kMaxMels];       // first bin of each filter's support
-  unsigned short mel_cnt[kMaxMels];      // support length
-  unsigned short mel_off[kMaxMels];      // offset of its weights in melw
-  unsigned short mel_begin[G::NW + 1];   // filters [mel_begin[w], mel_begin[w+1]) belong to warp w
+struct alignas(16) Tables {
+  float s1[G::N2 * G::S1_STRIDE];        // stage-1 constants per column b (S1_STRIDE % 4 == 0)
+  float melw[kMaxMelWeights];            // grouped filter weights
+  unsigned short mel_lo[kMaxMels];       // first bin read for each filter
+  unsigned short mel_begin[G::NWK + 1];
+  unsigned short mel_ng[G::NWK];
+  unsigned short mel_woff[G::NWK];       // in units of 4 weights
 };
 
 // ---------------------------------------------------------------------------------------
@@ -81,7 +98,7 @@ LM_HD float load_sample(const float* __restrict__ clip, long s, int n_samples, i
   return clip[s];
 }
 
-template <class G> LM_HD int wave_index(int r) { return r + r / G::HOP; }
+template <class G> LM_HD int wave_index(int r) { return r + 4 * (r / G::HOP); }
 
 // ---------------------------------------------------------------------------------------
 // loads / stores of the value type
@@ -135,21 +152,39 @@ template <> struct Codelets<1024> {
 };
 
 // ---------------------------------------------------------------------------------------
-// stage 1: column b of this lane's frame(s)
+// stage 1: one task = 8 frame slots x 4 adjacent columns
 // ---------------------------------------------------------------------------------------
-// wave_s: tile in shared memory (wave_index layout), Y: [k1][b][lane] as described in Geo.
+// Lane l of the warp handles frame slot p = 8*fg + (l & 7) (frames p and p+32 when packed) and
+// column b = 4*cg + (l >> 3).  With the 4-bank row stride the 32 lanes read 32 distinct banks.
+// Y[k1][b][slot]: the slot is XOR-swizzled with the column (slot = p ^ 8*(b & 3)) so that these
+// writes (4 columns x 8 slots) and the stage-2 reads (one column, 32 slots) are both conflict
+// free without padding.  s1tab may live in shared memory (device) or anywhere (host emulation).
+template <class G> LM_HD int y_slot(int p, int b) { return p ^ (8 * (b & 3)); }
+
 template <class G, typename T>
 LM_HD void stage1_task(const float* __restrict__ wave_s, T* __restrict__ Y,
-                       const float* __restrict__ s1tab, int b, int lane) {
+                       const float* __restrict__ s1tab, int task, int lane) {
   constexpr int N1 = G::N1, N2 = G::N2, H1 = G::H1;
-  const float* cst = s1tab + b * G::S1_STRIDE;
-  const float* src = wave_s + lane * G::PITCH + b;
+  const int cg = task % G::CGROUPS, fg = task / G::CGROUPS;
+  const int b = 4 * cg + (lane >> 3);
+  const int p = 8 * fg + (lane & 7);
+  const float* src = wave_s + p * G::PITCH + b;
+  // window samples and twiddles of this column: S1_STRIDE floats, fetched 16 bytes at a time
+  float cst[G::S1_STRIDE];
+  {
+    const float4* c4 = reinterpret_cast<const float4*>(s1tab + b * G::S1_STRIDE);
+#pragma unroll
+    for (int i = 0; i < G::S1_STRIDE / 4; ++i) {
+      const float4 v = c4[i];
+      cst[4 * i] = v.x; cst[4 * i + 1] = v.y; cst[4 * i + 2] = v.z; cst[4 * i + 3] = v.w;
+    }
+  }
   T x[N1];
   float w[N1], tr[H1 + 1], ti[H1 + 1];
 #pragma unroll
   for (int a = 0; a < N1; ++a) {
-    // sample n = N2*a + b of frame `lane`: r = HOP*lane + n, and n / HOP == (N2*a) / HOP
-    x[a] = VT<T>::load_wave(src + (N2 * a + (N2 * a) / G::HOP), 32 * G::PITCH);
+    // sample n = N2*a + b of frame p: r = HOP*p + n, and n / HOP == (N2*a) / HOP
+    x[a] = VT<T>::load_wave(src + (N2 * a + 4 * ((N2 * a) / G::HOP)), 32 * G::PITCH);
     w[a] = cst[a];
   }
   tr[0] = 1.0f;
@@ -161,14 +196,12 @@ LM_HD void stage1_task(const float* __restrict__ wave_s, T* __restrict__ Y,
   }
   T yr[H1 + 1], yi[H1 + 1];
   Codelets<G::N>::template s1<T>(x, w, tr, ti, yr, yi);
-  Y[b * 32 + lane] = yr[0];
-  T* yc = Y + G::Y0_ELEMS;
+  T* dre = Y + b * 32 + y_slot<G>(p, b);
+  T* dim = dre + G::YRE_ELEMS;
 #pragma unroll
-  for (int k = 1; k <= H1; ++k) {
-    T* d = yc + (((k - 1) * N2 + b) * 32 + lane) * 2;
-    d[0] = yr[k];
-    d[1] = yi[k];
-  }
+  for (int k = 0; k <= H1; ++k) dre[k * N2 * 32] = yr[k];
+#pragma unroll
+  for (int k = 1; k <= H1; ++k) dim[(k - 1) * N2 * 32] = yi[k];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -180,18 +213,19 @@ LM_HD void stage2_task(const T* __restrict__ Y, T* __restrict__ P, int k1, int l
   if (k1 == 0) {
     T yr[N2], p[N2 / 2 + 1];
 #pragma unroll
-    for (int b = 0; b < N2; ++b) yr[b] = Y[b * 32 + lane];
+    for (int b = 0; b < N2; ++b) yr[b] = Y[b * 32 + y_slot<G>(lane, b)];
     Codelets<N>::template s2_real<T>(yr, p);
 #pragma unroll
     for (int j = 0; j <= N2 / 2; ++j) P[(N1 * j) * 32 + lane] = p[j];
     return;
   }
   T yr[N2], yi[N2];
-  const T* yc = Y + G::Y0_ELEMS + ((k1 - 1) * N2 * 32 + lane) * 2;
+  const T* sre = Y + k1 * N2 * 32;
+  const T* sim = Y + G::YRE_ELEMS + (k1 - 1) * N2 * 32;
 #pragma unroll
   for (int b = 0; b < N2; ++b) {
-    yr[b] = yc[b * 64];
-    yi[b] = yc[b * 64 + 1];
+    yr[b] = sre[b * 32 + y_slot<G>(lane, b)];
+    yi[b] = sim[b * 32 + y_slot<G>(lane, b)];
   }
   if (k1 == H1) {
     T p[N2 / 2];
@@ -212,18 +246,83 @@ LM_HD void stage2_task(const T* __restrict__ Y, T* __restrict__ P, int k1, int l
 }
 
 // ---------------------------------------------------------------------------------------
-// mel projection for the filters owned by warp `w`: banded gather, one filter at a time
+// mel projection for the filters owned by warp `w`: grouped banded gather, two filters in flight
 // ---------------------------------------------------------------------------------------
+// NG > 0: group count known at compile time (straight-line code, the two filters of a pair
+// interleaved for ILP); NG == 0: run-time group count.  w4 points at the pair's weights:
+// ng float4 for the first filter, then ng float4 for the second.
+template <int NG, typename T>
+LM_HD void mel_dot2(const T* __restrict__ s0, const T* __restrict__ s1, const float4* __restrict__ w4,
+                    int ng, T& a0, T& a1) {
+  a0 = vzero<T>();
+  a1 = vzero<T>();
+  if (NG > 0) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float4 u = w4[g], v = w4[NG + g];
+      a0 = vfmas(s0[g * 128], u.x, a0);
+      a1 = vfmas(s1[g * 128], v.x, a1);
+      a0 = vfmas(s0[g * 128 + 32], u.y, a0);
+      a1 = vfmas(s1[g * 128 + 32], v.y, a1);
+      a0 = vfmas(s0[g * 128 + 64], u.z, a0);
+      a1 = vfmas(s1[g * 128 + 64], v.z, a1);
+      a0 = vfmas(s0[g * 128 + 96], u.w, a0);
+      a1 = vfmas(s1[g * 128 + 96], v.w, a1);
+    }
+  } else {
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+      const float4 u = w4[g], v = w4[ng + g];
+      a0 = vfmas(s0[g * 128], u.x, a0);
+      a1 = vfmas(s1[g * 128], v.x, a1);
+      a0 = vfmas(s0[g * 128 + 32], u.y, a0);
+      a1 = vfmas(s1[g * 128 + 32], v.y, a1);
+      a0 = vfmas(s0[g * 128 + 64], u.z, a0);
+      a1 = vfmas(s1[g * 128 + 64], v.z, a1);
+      a0 = vfmas(s0[g * 128 + 96], u.w, a0);
+      a1 = vfmas(s1[g * 128 + 96], v.w, a1);
+    }
+  }
+}
+
+// emit(acc) is called once per filter, in filter order
+template <int NG, class G, typename T, class Emit>
+LM_HD void mel_run(const T* __restrict__ P, const Tables<G>& tab, int m0, int m1, int ng, int woff,
+                   int lane, Emit&& emit) {
+  const T* Pl = P + lane;
+  const float4* w4 = reinterpret_cast<const float4*>(tab.melw) + woff;
+  int m = m0;
+#pragma unroll 1
+  for (; m + 1 < m1; m += 2, w4 += 2 * ng) {
+    T a0, a1;
+    mel_dot2<NG, T>(Pl + tab.mel_lo[m] * 32, Pl + tab.mel_lo[m + 1] * 32, w4, ng, a0, a1);
+    emit(a0);
+    emit(a1);
+  }
+  if (m < m1) {     // odd run length: the last filter alone
+    T a0 = vzero<T>();
+    const T* s = Pl + tab.mel_lo[m] * 32;
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+      const float4 u = w4[g];
+      a0 = vfmas(s[g * 128], u.x, a0);
+      a0 = vfmas(s[g * 128 + 32], u.y, a0);
+      a0 = vfmas(s[g * 128 + 64], u.z, a0);
+      a0 = vfmas(s[g * 128 + 96], u.w, a0);
+    }
+    emit(a0);
+  }
+}
+
 template <class G, typename T, class Emit>
 LM_HD void mel_task(const T* __restrict__ P, const Tables<G>& tab, int w, int lane, Emit&& emit) {
   const int m0 = tab.mel_begin[w], m1 = tab.mel_begin[w + 1];
-  for (int m = m0; m < m1; ++m) {
-    const int lo = tab.mel_lo[m], cnt = tab.mel_cnt[m];
-    const float* wp = tab.melw + tab.mel_off[m];
-    const T* src = P + lo * 32 + lane;
-    T acc = vzero<T>();
-    for (int j = 0; j < cnt; ++j) acc = vfmas(src[j * 32], wp[j], acc);
-    emit(m, acc);
+  const int ng = tab.mel_ng[w], woff = tab.mel_woff[w];
+  switch (ng) {      // warp-uniform
+    case 1: mel_run<1, G, T>(P, tab, m0, m1, 1, woff, lane, emit); break;
+    case 2: mel_run<2, G, T>(P, tab, m0, m1, 2, woff, lane, emit); break;
+    case 3: mel_run<3, G, T>(P, tab, m0, m1, 3, woff, lane, emit); break;
+    default: mel_run<0, G, T>(P, tab, m0, m1, ng, woff, lane, emit); break;
   }
 }
 

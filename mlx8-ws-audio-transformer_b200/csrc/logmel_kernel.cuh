@@ -28,64 +28,150 @@ struct KArgs {
   float log_add, log_floor, log_scale;   // y = log2(max(x + add, floor)) * scale
   int group, n_groups, tiles_per_clip;
   int vec_ok;        // slabs are float4-addressable
+  int tma_ok;        // every clip starts 16-byte aligned: tiles can be fetched with bulk copies
 };
 
 template <class G>
-struct Lay {   // shared-memory budget of one CTA
+struct Lay {   // dynamic shared-memory budget of one CTA: Y | P | waveform tile | stage-1 constants
   using T = typename ValT<G>::type;
   static constexpr size_t Y = (size_t)G::Y_ELEMS * sizeof(T);
   static constexpr size_t P = (size_t)G::P_ELEMS * sizeof(T);
   static constexpr size_t W = (size_t)G::WAVE_FLOATS * 4;
-  // when all three do not fit, P reuses the waveform buffer (dead after stage 1) and the next
-  // tile is fetched after the mel phase instead of behind it
-  static constexpr bool ALIAS = Y + P + W > 225 * 1024;
-  static constexpr size_t BYTES = ALIAS ? Y + (P > W ? P : W) : Y + P + W;
-  static constexpr int MIN_CTAS = BYTES <= 112 * 1024 ? 2 : 1;
+  static constexpr size_t S1 = (size_t)G::N2 * G::S1_STRIDE * 4;
+  // when all of it does not fit, P reuses the waveform buffer (dead after stage 1) and the next
+  // tile is fetched after the mel phase instead of behind stage 2
+  static constexpr bool ALIAS = Y + P + W + S1 > 222 * 1024;
+  static constexpr size_t PW = ALIAS ? (P > W ? P : W) : P + W;
+  static constexpr size_t BYTES = Y + PW + S1;
+  static constexpr int MIN_CTAS = BYTES <= 110 * 1024 ? 2 : 1;
 };
 
-__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
-template <class G>
-__device__ __forceinline__ void load_tile(float* wave_s, const float* __restrict__ clip, long long s0,
-                                          int n_samples, int valid) {
-  const bool fast = (s0 >= 0) && (s0 + G::SPAN <= (long long)valid);
-  if (fast) {
-    const float* src = clip + s0;
-    for (int r = threadIdx.x; r < G::SPAN; r += G::THREADS) cp_async4(wave_s + wave_index<G>(r), src + r);
-  } else {
-    for (int r = threadIdx.x; r < G::SPAN; r += G::THREADS)
-      wave_s[wave_index<G>(r)] = load_sample(clip, (long)(s0 + r), n_samples, valid);
-  }
-  cp_async_commit();
+// ---- TMA (bulk async copy) + mbarrier primitives -----------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(float* dst_smem, const float* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
+// Stage the SPAN samples of a tile into shared memory (wave_index layout).
+//
+// Interior tiles: ONE thread issues one TMA bulk copy per hop row (HOP*4 bytes, both addresses
+// 16-byte aligned) onto an mbarrier; no other thread spends an instruction on the waveform.
+// Tiles that touch a clip edge or the zero padding (and unaligned inputs) are filled by all
+// threads through load_sample (reflection / zero fill).
 template <class G>
+__device__ __forceinline__ bool tile_is_interior(long long s0, int valid) {
+  return (s0 >= 0) && (s0 + G::SPAN <= (long long)valid);
+}
+
+// called by all 32 lanes of the producer warp: lane 0 arms the mbarrier with the tile's byte
+// count, then every lane issues the bulk copies of rows lane, lane + 32, ... (a single thread
+// issuing all ~66 copies back to back would take longer than the phase it hides behind)
+template <class G>
+__device__ __forceinline__ void load_tile_tma(float* wave_s, const float* __restrict__ src, unsigned long long* bar,
+                                              int lane) {
+  constexpr int FULL_ROWS = G::SPAN / G::HOP;
+  constexpr int REM = G::SPAN - FULL_ROWS * G::HOP;
+  static_assert((G::HOP * 4) % 16 == 0 && (REM * 4) % 16 == 0 && (G::PITCH * 4) % 16 == 0, "bulk copies move 16-byte units");
+  fence_proxy_async();      // earlier generic-proxy reads of this buffer are ordered before the async writes
+  if (lane == 0) mbar_expect_tx(bar, (unsigned)G::SPAN * 4u);
+  __syncwarp();
+#pragma unroll 1
+  for (int row = lane; row < FULL_ROWS; row += 32) bulk_g2s(wave_s + row * G::PITCH, src + row * G::HOP, G::HOP * 4, bar);
+  if (REM > 0 && lane == (FULL_ROWS & 31)) bulk_g2s(wave_s + FULL_ROWS * G::PITCH, src + FULL_ROWS * G::HOP, REM * 4, bar);
+}
+
+template <class G, int NTHREADS>
+__device__ __forceinline__ void load_tile_edge(float* wave_s, const float* __restrict__ clip, long long s0,
+                                               int n_samples, int valid) {
+  for (int r = threadIdx.x; r < G::SPAN; r += NTHREADS)
+    wave_s[wave_index<G>(r)] = load_sample(clip, (long)(s0 + r), n_samples, valid);
+}
+
+// every sample the tile touches (after reflection about the padded length) is zero padding
+template <class G>
+__device__ __forceinline__ bool tile_is_silent(long long s0, int n_samples, int valid) {
+  if (s0 < valid) return false;
+  const long long last = s0 + G::SPAN - 1;
+  if (last < n_samples) return true;
+  return 2LL * (n_samples - 1) - last >= valid;
+}
+
+constexpr int kMaxLocalTiles = 64;
+
+// KIND: 0 = mel power, 1 = log10(max(x, floor)), 2 = ln(x + eps), 3 = Whisper: kind 1 followed by
+// max(S, clipmax - 8), (S + 4) / 4.
+//
+// Whisper normalisation without a second pass over the data: g(S) = (S + 4) * 0.25 is
+// monotone, so max(g(S), g(M - 8)) == g(max(S, M - 8)) bit for bit.  The first pass therefore
+// stores g(S) -- already final wherever S >= M - 8 -- and records each tile's minimum; once the
+// clip group has agreed on M, only tiles whose minimum lies below M - 8 are revisited with
+// out = max(out, g(M - 8)), while their lines are still in L2.  Silent tiles (all zero padding)
+// are not computed at all: their constant is written once, after M is known.
+template <class G, int KIND>
 __global__ void __launch_bounds__(G::THREADS, Lay<G>::MIN_CTAS)
 logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
   using T = typename ValT<G>::type;
   constexpr bool ALIAS = Lay<G>::ALIAS;
+  constexpr bool NORM = KIND == 3;
+  constexpr int NT = G::THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Y = reinterpret_cast<T*>(smem_raw);
   T* P = Y + G::Y_ELEMS;
   float* wave_s = ALIAS ? reinterpret_cast<float*>(P) : reinterpret_cast<float*>(P + G::P_ELEMS);
-  __shared__ float s_red[G::NW];
+  float* s1_s = reinterpret_cast<float*>(smem_raw + Lay<G>::Y + Lay<G>::PW);
+  __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ float s_red[G::NWK];
   __shared__ float s_max;
+  __shared__ float s_tmin[NORM ? kMaxLocalTiles : 1][G::NWK];
+  __shared__ unsigned char s_silent[NORM ? kMaxLocalTiles : 1];
 
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const bool producer = warp == G::NW;
   const int group_id = blockIdx.x / a.group;
   const int rank = blockIdx.x - group_id * a.group;
-  const bool use_log = a.log_mode != LOG_NONE;
+  const float log_floor = a.log_floor, log_add = a.log_add, log_scale = a.log_scale;
+  // what a bin-wise silent frame produces, through exactly the arithmetic of the mel phase
+  float silent_val = 0.0f;
+  if (KIND == 1 || KIND == 3) silent_val = vlog2_clamp(0.0f, log_floor) * log_scale;
+  if (KIND == 2) silent_val = vlog2_add(0.0f, log_add) * log_scale;
+
+  // one-time setup: stage-1 constants into shared memory (the four column groups of a warp read
+  // four different rows of the table at once), mbarrier for the TMA tile copies
+  for (int i = threadIdx.x; i < G::N2 * G::S1_STRIDE; i += NT) s1_s[i] = tab.s1[i];
+  if (threadIdx.x == 0) {
+    mbar_init(&s_mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned parity = 0;
 
   for (int clip = group_id; clip < a.batch; clip += a.n_groups) {
     const float* cptr = a.wave + (long long)clip * a.clip_stride;
@@ -94,59 +180,119 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
     float* oc = a.out + (long long)clip * a.n_mels * a.n_frames;
     const int t0 = (int)((long long)rank * a.tiles_per_clip / a.group);
     const int t1 = (int)((long long)(rank + 1) * a.tiles_per_clip / a.group);
+    const bool track = NORM && (t1 - t0 <= kMaxLocalTiles);
     float rmax = -INFINITY;
+    int staged = -1;          // tile whose waveform is in (or on its way into) wave_s
+    bool staged_tma = false;  // ... and whether it arrives through the mbarrier
 
-    if (t0 < t1) {
-      load_tile<G>(wave_s, cptr, (long long)t0 * G::F * G::HOP - G::N / 2, a.n_samples, valid);
-      cp_async_wait_all();
-    }
-    __syncthreads();
+    // CTA-uniform: start filling wave_s with the tile that begins at sample s
+    auto fetch = [&](long long s) -> bool {
+      const bool tma = a.tma_ok && tile_is_interior<G>(s, valid);
+      if (tma) {
+        if (producer) load_tile_tma<G>(wave_s, cptr + s, &s_mbar, lane);
+      } else {
+        load_tile_edge<G, NT>(wave_s, cptr, s, a.n_samples, valid);
+      }
+      return tma;
+    };
 
+    // Per computed tile: [stage 1] barrier [TMA prefetch | stage 2] barrier [mel].  The mel phase
+    // of tile t and stage 1 of the next tile share an interval, so uneven filter runs are absorbed.
     for (int t = t0; t < t1; ++t) {
       const int f0 = t * G::F;
-      // ---- stage 1: columns b = warp, warp + NW, ...
+      const long long s0 = (long long)f0 * G::HOP - G::N / 2;
+      if (tile_is_silent<G>(s0, a.n_samples, valid)) {          // CTA-uniform
+        rmax = fmaxf(rmax, silent_val);
+        if (NORM) {
+          if (track && threadIdx.x == 0) s_silent[t - t0] = 1;
+        } else {
+          // no normalisation: the constant can be written right away
+          const int fend = min(f0 + G::F, a.n_frames);
+          for (int m = warp; m < a.n_mels; m += G::NWK)
+            for (int f = f0 + lane; f < fend; f += 32) oc[(long long)m * a.n_frames + f] = silent_val;
+        }
+        continue;
+      }
+      if (NORM && track && threadIdx.x == 0) s_silent[t - t0] = 0;
+      if (staged != t) {                                        // first tile of a run: fetch it now
+        staged_tma = fetch(s0);
+        if (!staged_tma) __syncthreads();
+      }
+      if (staged_tma) {                                         // the bulk copies have landed
+        mbar_wait(&s_mbar, parity);
+        parity ^= 1u;
+      }
+      // ---- stage 1: S1_TASKS / NW tasks of (8 frame slots x 4 columns) per warp
+      if (!producer) {
 #pragma unroll 1
-      for (int b = warp; b < G::N2; b += G::NW) stage1_task<G, T>(wave_s, Y, tab.s1, b, lane);
-      __syncthreads();
-      // the waveform tile is dead: prefetch the next one behind stage 2 and the mel phase
-      if (!ALIAS && t + 1 < t1)
-        load_tile<G>(wave_s, cptr, (long long)(t + 1) * G::F * G::HOP - G::N / 2, a.n_samples, valid);
-      // ---- stage 2: rows k1 = 1..H1-1 on warps 0..NW-2, the two half-size rows on the last warp
-      if (warp < G::NW - 1) {
-        stage2_task<G, T>(Y, P, warp + 1, lane);
-      } else {
-        stage2_task<G, T>(Y, P, 0, lane);
-        stage2_task<G, T>(Y, P, G::H1, lane);
+        for (int task = warp; task < G::S1_TASKS; task += G::NW) stage1_task<G, T>(wave_s, Y, s1_s, task, lane);
       }
       __syncthreads();
-      // ---- mel projection, log, store of the un-normalised value, running max
-      mel_task<G, T>(P, tab, warp, lane, [&](int m, T acc) {
-        float v0 = vlo(acc), v1 = vhi(acc);
-        if (use_log) {
-          v0 = __log2f(fmaxf(v0 + a.log_add, a.log_floor)) * a.log_scale;
-          if (G::PK == 2) v1 = __log2f(fmaxf(v1 + a.log_add, a.log_floor)) * a.log_scale;
-        }
+      // ---- the waveform tile is dead: fetch the next one behind stage 2
+      const long long s1 = s0 + (long long)G::F * G::HOP;
+      const bool next_needed = (t + 1 < t1) && !tile_is_silent<G>(s1, a.n_samples, valid);
+      if (!ALIAS && next_needed) {
+        staged_tma = fetch(s1);
+        staged = t + 1;
+      }
+      // ---- stage 2: rows k1 = 1..H1-1 on warps 0..NW-2, the real row 0 on warp NW-1 and the
+      //      half row H1 on the producer warp (behind its copy instructions)
+      stage2_task<G, T>(Y, P, warp < G::NW - 1 ? warp + 1 : (producer ? G::H1 : 0), lane);
+      __syncthreads();
+      // ---- mel projection, log, store, running max / tile min (all NWK warps)
+      {
         const int f = f0 + lane;
-        float* o = oc + (long long)m * a.n_frames + f;
-        if (f < a.n_frames) {
-          o[0] = v0;
-          rmax = fmaxf(rmax, v0);
+        const bool full = f0 + G::F <= a.n_frames;            // CTA-uniform: only a clip's last tile is not
+        float* op = oc + (long long)tab.mel_begin[warp] * a.n_frames + f;
+        const long long ostep = a.n_frames;
+        float tmin = INFINITY;
+        if (full) {
+          mel_task<G, T>(P, tab, warp, lane, [&](T acc) {
+            T v = acc;
+            if (KIND == 1 || KIND == 3) v = vmuls(vlog2_clamp(v, log_floor), log_scale);
+            if (KIND == 2) v = vmuls(vlog2_add(v, log_add), log_scale);
+            if (NORM) {
+              rmax = vhmax(rmax, v);
+              tmin = vhmin(tmin, v);
+              v = vmulc(vadds(v, 4.0f), 0.25f);
+            }
+            op[0] = vlo(v);
+            if (G::PK == 2) op[32] = vhi(v);
+            op += ostep;
+          });
+        } else {
+          const bool ok0 = f < a.n_frames, ok1 = (G::PK == 2) && (f + 32 < a.n_frames);
+          mel_task<G, T>(P, tab, warp, lane, [&](T acc) {
+            T v = acc;
+            if (KIND == 1 || KIND == 3) v = vmuls(vlog2_clamp(v, log_floor), log_scale);
+            if (KIND == 2) v = vmuls(vlog2_add(v, log_add), log_scale);
+            if (NORM) {
+              if (ok0) { rmax = fmaxf(rmax, vlo(v)); tmin = fminf(tmin, vlo(v)); }
+              if (ok1) { rmax = fmaxf(rmax, vhi(v)); tmin = fminf(tmin, vhi(v)); }
+              v = vmulc(vadds(v, 4.0f), 0.25f);
+            }
+            if (ok0) op[0] = vlo(v);
+            if (ok1) op[32] = vhi(v);
+            op += ostep;
+          });
         }
-        if (G::PK == 2 && f + 32 < a.n_frames) {
-          o[32] = v1;
-          rmax = fmaxf(rmax, v1);
+        if (track) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+          if (lane == 0) s_tmin[t - t0][warp] = tmin;
         }
-      });
-      if (ALIAS) {
-        __syncthreads();   // P shares the waveform buffer: reload only after the mel phase
-        if (t + 1 < t1)
-          load_tile<G>(wave_s, cptr, (long long)(t + 1) * G::F * G::HOP - G::N / 2, a.n_samples, valid);
       }
-      cp_async_wait_all();
-      __syncthreads();
+      if (ALIAS) {
+        __syncthreads();   // P shares the waveform buffer: the next tile is fetched only now
+        if (next_needed) {
+          staged_tma = fetch(s1);
+          staged = t + 1;
+          if (!staged_tma) __syncthreads();
+        }
+      }
     }
 
-    if (a.log_mode == LOG10_CLAMP_WHISPER_NORM) {
+    if (NORM) {
       // ---- clip maximum: warp shuffle -> CTA -> clip group (release/acquire counter)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
@@ -154,7 +300,7 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
       __syncthreads();
       if (threadIdx.x == 0) {
         float m = s_red[0];
-        for (int w = 1; w < G::NW; ++w) m = fmaxf(m, s_red[w]);
+        for (int w = 1; w < G::NWK; ++w) m = fmaxf(m, s_red[w]);
         if (a.group > 1) {
           float* slots = a.gmax + (long long)clip * a.group;
           __stcg(slots + rank, m);
@@ -167,33 +313,50 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
         s_max = m;
       }
       __syncthreads();
-      // ---- normalise this CTA's slab in place (still L2 resident)
+      // ---- revisit only what the clamp actually touches
       const float thr = s_max - 8.0f;
-      const int fa = t0 * G::F;
-      const int fb = min(t1 * G::F, a.n_frames);
-      const int len = fb - fa;
-      if (len > 0) {
-        if (a.vec_ok) {
-          const int q = len >> 2;
-          for (int m = warp; m < a.n_mels; m += G::NW) {
-            float4* row = reinterpret_cast<float4*>(oc + (long long)m * a.n_frames + fa);
-            for (int j = lane; j < q; j += 32) {
-              float4 v = __ldcg(row + j);
-              v.x = (fmaxf(v.x, thr) + 4.0f) * 0.25f;
-              v.y = (fmaxf(v.y, thr) + 4.0f) * 0.25f;
-              v.z = (fmaxf(v.z, thr) + 4.0f) * 0.25f;
-              v.w = (fmaxf(v.w, thr) + 4.0f) * 0.25f;
-              __stcs(row + j, v);
-            }
-          }
+      const float cval = (thr + 4.0f) * 0.25f;
+      const float sval = (fmaxf(silent_val, thr) + 4.0f) * 0.25f;
+      for (int t = t0; t < t1; ++t) {
+        const int fa = t * G::F;
+        const int len = min(fa + G::F, a.n_frames) - fa;
+        bool silent, fix;
+        if (track) {
+          silent = s_silent[t - t0] != 0;
+          float tm = INFINITY;
+          if (!silent)
+            for (int w = 0; w < G::NWK; ++w) tm = fminf(tm, s_tmin[t - t0][w]);
+          fix = tm < thr;
         } else {
-          for (int m = warp; m < a.n_mels; m += G::NW) {
+          silent = tile_is_silent<G>((long long)fa * G::HOP - G::N / 2, a.n_samples, valid);
+          fix = true;
+        }
+        if (silent) {
+          for (int m = warp; m < a.n_mels; m += G::NWK) {
             float* row = oc + (long long)m * a.n_frames + fa;
-            for (int j = lane; j < len; j += 32) row[j] = (fmaxf(__ldcg(row + j), thr) + 4.0f) * 0.25f;
+            for (int j = lane; j < len; j += 32) __stcs(row + j, sval);
+          }
+        } else if (fix) {
+          if (a.vec_ok && (len & 3) == 0) {
+            const int q = len >> 2;          // <= 16 float4 per row: two rows per warp pass
+            for (int m = 2 * warp + (lane >> 4); m < a.n_mels; m += 2 * G::NWK) {
+              float4* row = reinterpret_cast<float4*>(oc + (long long)m * a.n_frames + fa);
+              const int j = lane & 15;
+              if (j < q) {
+                float4 v = __ldcg(row + j);
+                v.x = fmaxf(v.x, cval); v.y = fmaxf(v.y, cval); v.z = fmaxf(v.z, cval); v.w = fmaxf(v.w, cval);
+                __stcs(row + j, v);
+              }
+            }
+          } else {
+            for (int m = warp; m < a.n_mels; m += G::NWK) {
+              float* row = oc + (long long)m * a.n_frames + fa;
+              for (int j = lane; j < len; j += 32) row[j] = fmaxf(__ldcg(row + j), cval);
+            }
           }
         }
       }
-      __syncthreads();   // s_red / s_max are reused by the next clip
+      __syncthreads();   // s_red / s_max / s_tmin are reused by the next clip
     }
   }
 }

@@ -1,6 +1,7 @@
 // Host-side construction of the constant tables the kernel reads from its parameter bank.
 // Plain C++ (no CUDA): shared by the C-ABI library and by the host emulation in tests/.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -34,38 +35,58 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
       c[G::N1 + 2 * (k - 1) + 1] = (float)std::sin(ang);
     }
   }
-  int off = 0;
-  std::vector<int> cost(n_mels);
+  // ---- banded supports
+  std::vector<int> lo(n_mels, 0), cnt(n_mels, 0);
   for (int m = 0; m < n_mels; ++m) {
-    int lo = -1, hi = -1;
-    for (int k = 0; k < G::NBINS; ++k) {
+    int first = -1, last = -1;
+    for (int k = 0; k < G::NBINS; ++k)
       if (fbank[(size_t)k * n_mels + m] != 0.0f) {
-        if (lo < 0) lo = k;
-        hi = k + 1;
+        if (first < 0) first = k;
+        last = k;
       }
+    if (first >= 0) {
+      lo[m] = first;
+      cnt[m] = last - first + 1;
     }
-    if (lo < 0) lo = hi = 0;
-    const int cnt = hi - lo;
-    if (off + cnt > kMaxMelWeights) return "filter bank is not banded enough (more than 2048 weights)";
-    t.mel_lo[m] = (unsigned short)lo;
-    t.mel_cnt[m] = (unsigned short)cnt;
-    t.mel_off[m] = (unsigned short)off;
-    for (int j = 0; j < cnt; ++j) t.melw[off + j] = fbank[(size_t)(lo + j) * n_mels + m];
-    off += cnt;
-    cost[m] = cnt + 8;   // + clamp/log/max/store
   }
-  // contiguous runs of filters per warp, balanced on cost
+  // ---- contiguous runs of filters per warp, balanced on (groups of 4 weights) + epilogue cost
+  std::vector<long> cost(n_mels);
   long total = 0;
-  for (int m = 0; m < n_mels; ++m) total += cost[m];
-  int m = 0;
-  long acc = 0;
-  t.mel_begin[0] = 0;
-  for (int w = 0; w < G::NW; ++w) {
-    const long target = total * (w + 1) / G::NW;
-    while (m < n_mels && (acc + cost[m] / 2 <= target || w == G::NW - 1)) acc += cost[m++];
-    t.mel_begin[w + 1] = (unsigned short)m;
+  for (int m = 0; m < n_mels; ++m) total += (cost[m] = 9L * std::max(1, (cnt[m] + 3) / 4) + 14);
+  {
+    int m = 0;
+    long acc = 0;
+    t.mel_begin[0] = 0;
+    for (int w = 0; w < G::NWK; ++w) {
+      const long target = total * (w + 1) / G::NWK;
+      while (m < n_mels && (acc + cost[m] / 2 <= target || w == G::NWK - 1)) acc += cost[m++];
+      t.mel_begin[w + 1] = (unsigned short)m;
+    }
+    t.mel_begin[G::NWK] = (unsigned short)n_mels;
   }
-  t.mel_begin[G::NW] = (unsigned short)n_mels;
+  // ---- grouped, zero padded weights; a run uses the group count of its widest filter
+  int off = 0;
+  for (int w = 0; w < G::NWK; ++w) {
+    const int m0 = t.mel_begin[w], m1 = t.mel_begin[w + 1];
+    int ng = 1;
+    for (int m = m0; m < m1; ++m) ng = std::max(ng, (cnt[m] + 3) / 4);
+    if (4 * ng > G::NBINS) return "filter bank is not banded (a support is wider than the spectrum)";
+    if (off + (m1 - m0) * 4 * ng > kMaxMelWeights)
+      return "filter bank is not banded enough (grouped weights exceed 3072)";
+    t.mel_ng[w] = (unsigned short)ng;
+    t.mel_woff[w] = (unsigned short)(off / 4);
+    for (int m = m0; m < m1; ++m) {
+      // keep the 4*ng bins that are read inside the spectrum: shift the window down if needed
+      int start = lo[m];
+      if (start + 4 * ng > G::NBINS) start = G::NBINS - 4 * ng;
+      t.mel_lo[m] = (unsigned short)start;
+      for (int j = 0; j < 4 * ng; ++j) {
+        const int k = start + j;
+        t.melw[off + j] = (k >= lo[m] && k < lo[m] + cnt[m]) ? fbank[(size_t)k * n_mels + m] : 0.0f;
+      }
+      off += 4 * ng;
+    }
+  }
   return std::string();
 }
 

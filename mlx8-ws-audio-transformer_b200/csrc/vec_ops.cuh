@@ -18,6 +18,10 @@
 #define LM_D inline
 #endif
 
+#if !defined(__CUDACC__)
+struct alignas(16) float4 { float x, y, z, w; };   // host emulation build only
+#endif
+
 namespace lm {
 
 struct f32x2 {
@@ -92,6 +96,28 @@ LM_HD f32x2 vfma(f32x2 a, f32x2 b, f32x2 c) {
 #endif
 
 template <> LM_HD f32x2 vzero<f32x2>() { return vpack(0.0f, 0.0f); }
+
+// ---- epilogue helpers: log2 of a clamped / offset value, horizontal max / min ------------
+LM_HD float lm_log2(float x) {   // x is a normal positive number here
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return __builtin_log2f(x);
+#endif
+}
+LM_HD float vlog2_clamp(float v, float floor) { return lm_log2(__builtin_fmaxf(v, floor)); }
+LM_HD f32x2 vlog2_clamp(f32x2 v, float floor) {
+  return vpack(lm_log2(__builtin_fmaxf(vlo(v), floor)), lm_log2(__builtin_fmaxf(vhi(v), floor)));
+}
+LM_HD float vlog2_add(float v, float add) { return lm_log2(v + add); }
+LM_HD f32x2 vlog2_add(f32x2 v, float add) { return vpack(lm_log2(vlo(v) + add), lm_log2(vhi(v) + add)); }
+LM_HD float vhmax(float r, float v) { return __builtin_fmaxf(r, v); }
+LM_HD float vhmax(float r, f32x2 v) { return __builtin_fmaxf(r, __builtin_fmaxf(vlo(v), vhi(v))); }
+LM_HD float vhmin(float r, float v) { return __builtin_fminf(r, v); }
+LM_HD float vhmin(float r, f32x2 v) { return __builtin_fminf(r, __builtin_fminf(vlo(v), vhi(v))); }
+LM_HD float vadds(float a, float s) { return a + s; }
 LM_HD f32x2 vneg(f32x2 a) { return vmul(a, vpack(-1.0f, -1.0f)); }
 LM_HD f32x2 vmulc(f32x2 a, float k) { return vmul(a, vpack(k, k)); }
 LM_HD f32x2 vfmac(f32x2 a, float k, f32x2 c) { return vfma(a, vpack(k, k), c); }
@@ -99,5 +125,6 @@ LM_HD f32x2 vfnma(f32x2 a, f32x2 b, f32x2 c) { return vfma(vneg(a), b, c); }
 LM_HD f32x2 vmuls(f32x2 a, float s) { return vmul(a, vpack(s, s)); }
 LM_HD f32x2 vfmas(f32x2 a, float s, f32x2 c) { return vfma(a, vpack(s, s), c); }
 LM_HD f32x2 vfnmas(f32x2 a, float s, f32x2 c) { return vfma(a, vpack(-s, -s), c); }
+LM_HD f32x2 vadds(f32x2 a, float s) { return vadd(a, vpack(s, s)); }
 
 }  // namespace lm

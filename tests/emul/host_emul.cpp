@@ -54,21 +54,16 @@ int run(const float* wave, long batch, long stride, const int32_t* lengths, int 
       for (int r = 0; r < G::SPAN; ++r)
         wave_s[wave_index<G>(r)] = load_sample(clip, s0 + r, n_samples, valid);
       for (int w = 0; w < G::NW; ++w)
-        for (int b = w; b < G::N2; b += G::NW)
+        for (int task = w; task < G::S1_TASKS; task += G::NW)
           for (int lane = 0; lane < 32; ++lane)
-            stage1_task<G, T>(wave_s.data(), Y.data(), tab.s1, b, lane);
-      for (int w = 0; w < G::NW; ++w)
-        for (int lane = 0; lane < 32; ++lane) {
-          if (w < G::NW - 1) {
-            stage2_task<G, T>(Y.data(), P.data(), w + 1, lane);
-          } else {
-            stage2_task<G, T>(Y.data(), P.data(), 0, lane);
-            stage2_task<G, T>(Y.data(), P.data(), G::H1, lane);
-          }
-        }
-      for (int w = 0; w < G::NW; ++w)
+            stage1_task<G, T>(wave_s.data(), Y.data(), tab.s1, task, lane);
+      for (int w = 0; w < G::NWK; ++w)       // warp w < NW-1: row w+1; warp NW-1: row 0; producer: row H1
         for (int lane = 0; lane < 32; ++lane)
-          mel_task<G, T>(P.data(), tab, w, lane, [&](int m, T acc) {
+          stage2_task<G, T>(Y.data(), P.data(), w < G::NW - 1 ? w + 1 : (w == G::NW - 1 ? 0 : G::H1), lane);
+      for (int w = 0; w < G::NWK; ++w)
+        for (int lane = 0; lane < 32; ++lane) {
+          int m = tab.mel_begin[w];
+          mel_task<G, T>(P.data(), tab, w, lane, [&](T acc) {
             const float v[2] = {vlo(acc), vhi(acc)};
             for (int h = 0; h < G::PK; ++h) {
               const int f = f0 + lane + 32 * h;
@@ -77,7 +72,9 @@ int run(const float* wave, long batch, long stride, const int32_t* lengths, int 
               oc[(long)m * n_frames + f] = s;
               cmax = std::max(cmax, s);
             }
+            ++m;
           });
+        }
     }
     if (log_mode == LOG10_CLAMP_WHISPER_NORM) {
       const float thr = cmax - 8.0f;
