@@ -260,6 +260,11 @@ int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_st
   choose_grid(h, batch, a.tiles_per_clip, &a.group, &a.n_groups);
   a.vec_ok = (n_frames % 4 == 0) && (((uintptr_t)d_out & 15) == 0);
   a.tma_ok = (((uintptr_t)d_wave & 15) == 0) && (clip_stride % 4 == 0);
+  a.timeline = nullptr;
+#ifdef LM_TIMELINE
+  a.timeline = reinterpret_cast<long long*>(d_clip_max);   // debug build: d_clip_max carries the stamp buffer
+  a.clip_max = nullptr;
+#endif
   if (norm) {
     a.gcnt = reinterpret_cast<int*>(d_scratch);
     a.gmax = reinterpret_cast<float*>(d_scratch) + ((batch + 3) / 4) * 4;

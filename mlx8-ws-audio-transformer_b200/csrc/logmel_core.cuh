@@ -40,9 +40,14 @@ struct Geo {
   static constexpr int N1 = Split<NFFT>::N1, N2 = Split<NFFT>::N2;
   static constexpr int H1 = N1 / 2;                 // stage-2 tasks are k1 = 0..H1
   static constexpr int NBINS = N / 2 + 1;
-  static constexpr int NW = H1;                     // warps that share stage 1 (N2 / NW columns each)
-  static constexpr int NWK = NW + 1;                // + the producer warp: loads tiles, takes the
-                                                    //   k1 = H1 row of stage 2 and a run of filters
+  // Warps per CTA: a multiple of 4 so that every SM sub-partition (warp id mod 4) holds the
+  // same number of warps; the work tables below balance tasks per sub-partition.
+  static constexpr int NWK = (NFFT == 400) ? 11 : 16;
+  // N = 400: a warp's stage-1 tasks all use the same four columns, so their window samples and
+  // twiddles (S1_STRIDE floats per lane) are loaded once per kernel and stay in registers; the
+  // alternative -- fetching them from shared memory per task -- costs as many LSU wavefronts as
+  // the waveform samples themselves.  N = 1024 has too many constants (64) for that.
+  static constexpr bool S1_CONST_REGS = (NFFT == 400);
   static constexpr int THREADS = NWK * 32;
   static constexpr int F = 32 * PK;                 // frames per tile
   static constexpr int SPAN = (F - 1) * HOP + N;    // samples a tile touches
@@ -64,7 +69,9 @@ struct Geo {
   static_assert(HOP % 32 == 0, "the row pitch must be 4 banks past a multiple of 32");
   static constexpr int CGROUPS = N2 / 4;            // stage-1 tasks: (4 frame octets) x (N2/4 column quads)
   static constexpr int S1_TASKS = 4 * CGROUPS;
-  static_assert(N2 % 4 == 0 && S1_TASKS % NW == 0, "stage-1 tasks must divide evenly over the warps");
+  static constexpr int S1_MAX = 3, S2_MAX = 2;      // most tasks / rows one warp can be handed
+  static_assert(N2 % 4 == 0, "columns are handled four at a time");
+  static_assert(S1_TASKS <= NWK * S1_MAX && H1 + 1 <= NWK * S2_MAX, "work tables too small");
 };
 
 // kernel parameters that live in the constant bank (__grid_constant__)
@@ -82,6 +89,8 @@ struct alignas(16) Tables {
   unsigned short mel_begin[G::NWK + 1];
   unsigned short mel_ng[G::NWK];
   unsigned short mel_woff[G::NWK];       // in units of 4 weights
+  signed char s1_tasks[G::NWK][G::S1_MAX];   // stage-1 tasks of each warp (-1: none)
+  signed char s2_rows[G::NWK][G::S2_MAX];    // stage-2 rows k1 of each warp (-1: none)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -161,24 +170,26 @@ template <> struct Codelets<1024> {
 // free without padding.  s1tab may live in shared memory (device) or anywhere (host emulation).
 template <class G> LM_HD int y_slot(int p, int b) { return p ^ (8 * (b & 3)); }
 
+template <class G>
+LM_HD void stage1_consts(const float* __restrict__ s1tab, int task, int lane, float (&cst)[G::S1_STRIDE]) {
+  // window samples and twiddles of this lane's column: S1_STRIDE floats, fetched 16 bytes at a time
+  const int b = 4 * (task % G::CGROUPS) + (lane >> 3);
+  const float4* c4 = reinterpret_cast<const float4*>(s1tab + b * G::S1_STRIDE);
+#pragma unroll
+  for (int i = 0; i < G::S1_STRIDE / 4; ++i) {
+    const float4 v = c4[i];
+    cst[4 * i] = v.x; cst[4 * i + 1] = v.y; cst[4 * i + 2] = v.z; cst[4 * i + 3] = v.w;
+  }
+}
+
 template <class G, typename T>
-LM_HD void stage1_task(const float* __restrict__ wave_s, T* __restrict__ Y,
-                       const float* __restrict__ s1tab, int task, int lane) {
+LM_HD void stage1_task_c(const float* __restrict__ wave_s, T* __restrict__ Y,
+                         const float (&cst)[G::S1_STRIDE], int task, int lane) {
   constexpr int N1 = G::N1, N2 = G::N2, H1 = G::H1;
   const int cg = task % G::CGROUPS, fg = task / G::CGROUPS;
   const int b = 4 * cg + (lane >> 3);
   const int p = 8 * fg + (lane & 7);
   const float* src = wave_s + p * G::PITCH + b;
-  // window samples and twiddles of this column: S1_STRIDE floats, fetched 16 bytes at a time
-  float cst[G::S1_STRIDE];
-  {
-    const float4* c4 = reinterpret_cast<const float4*>(s1tab + b * G::S1_STRIDE);
-#pragma unroll
-    for (int i = 0; i < G::S1_STRIDE / 4; ++i) {
-      const float4 v = c4[i];
-      cst[4 * i] = v.x; cst[4 * i + 1] = v.y; cst[4 * i + 2] = v.z; cst[4 * i + 3] = v.w;
-    }
-  }
   T x[N1];
   float w[N1], tr[H1 + 1], ti[H1 + 1];
 #pragma unroll
@@ -202,6 +213,14 @@ LM_HD void stage1_task(const float* __restrict__ wave_s, T* __restrict__ Y,
   for (int k = 0; k <= H1; ++k) dre[k * N2 * 32] = yr[k];
 #pragma unroll
   for (int k = 1; k <= H1; ++k) dim[(k - 1) * N2 * 32] = yi[k];
+}
+
+template <class G, typename T>
+LM_HD void stage1_task(const float* __restrict__ wave_s, T* __restrict__ Y,
+                       const float* __restrict__ s1tab, int task, int lane) {
+  float cst[G::S1_STRIDE];
+  stage1_consts<G>(s1tab, task, lane, cst);
+  stage1_task_c<G, T>(wave_s, Y, cst, task, lane);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -29,7 +29,16 @@ struct KArgs {
   int group, n_groups, tiles_per_clip;
   int vec_ok;        // slabs are float4-addressable
   int tma_ok;        // every clip starts 16-byte aligned: tiles can be fetched with bulk copies
+  long long* timeline;   // debug builds (-DLM_TIMELINE): per-tile clock stamps of CTA 0, else NULL
 };
+
+#ifdef LM_TIMELINE
+#define LM_STAMP(slot)                                                                         \
+  if (a.timeline && blockIdx.x == 0 && lane == 0 && tl_tile < 48)                              \
+    a.timeline[(tl_tile * 16 + warp) * 8 + (slot)] = clock64();
+#else
+#define LM_STAMP(slot)
+#endif
 
 template <class G>
 struct Lay {   // dynamic shared-memory budget of one CTA: Y | P | waveform tile | stage-1 constants
@@ -37,7 +46,7 @@ struct Lay {   // dynamic shared-memory budget of one CTA: Y | P | waveform tile
   static constexpr size_t Y = (size_t)G::Y_ELEMS * sizeof(T);
   static constexpr size_t P = (size_t)G::P_ELEMS * sizeof(T);
   static constexpr size_t W = (size_t)G::WAVE_FLOATS * 4;
-  static constexpr size_t S1 = (size_t)G::N2 * G::S1_STRIDE * 4;
+  static constexpr size_t S1 = G::S1_CONST_REGS ? 0 : (size_t)G::N2 * G::S1_STRIDE * 4;
   // when all of it does not fit, P reuses the waveform buffer (dead after stage 1) and the next
   // tile is fetched after the mel phase instead of behind stage 2
   static constexpr bool ALIAS = Y + P + W + S1 > 222 * 1024;
@@ -90,21 +99,23 @@ __device__ __forceinline__ bool tile_is_interior(long long s0, int valid) {
   return (s0 >= 0) && (s0 + G::SPAN <= (long long)valid);
 }
 
-// called by all 32 lanes of the producer warp: lane 0 arms the mbarrier with the tile's byte
-// count, then every lane issues the bulk copies of rows lane, lane + 32, ... (a single thread
-// issuing all ~66 copies back to back would take longer than the phase it hides behind)
+// Called by every warp of the CTA: lane 0 of warp w issues the bulk copies of rows w, w + NWK,
+// ... (UBLKCP takes warp-uniform operands, so spreading rows over warps -- not lanes -- is what
+// issues them in parallel); warp 0 arms the mbarrier with the tile's byte count.
 template <class G>
 __device__ __forceinline__ void load_tile_tma(float* wave_s, const float* __restrict__ src, unsigned long long* bar,
-                                              int lane) {
+                                              int warp, int lane) {
   constexpr int FULL_ROWS = G::SPAN / G::HOP;
   constexpr int REM = G::SPAN - FULL_ROWS * G::HOP;
   static_assert((G::HOP * 4) % 16 == 0 && (REM * 4) % 16 == 0 && (G::PITCH * 4) % 16 == 0, "bulk copies move 16-byte units");
-  fence_proxy_async();      // earlier generic-proxy reads of this buffer are ordered before the async writes
-  if (lane == 0) mbar_expect_tx(bar, (unsigned)G::SPAN * 4u);
-  __syncwarp();
+  if (lane == 0) {
+    fence_proxy_async();    // earlier generic-proxy reads of this buffer are ordered before the async writes
+    if (warp == 0) mbar_expect_tx(bar, (unsigned)G::SPAN * 4u);
 #pragma unroll 1
-  for (int row = lane; row < FULL_ROWS; row += 32) bulk_g2s(wave_s + row * G::PITCH, src + row * G::HOP, G::HOP * 4, bar);
-  if (REM > 0 && lane == (FULL_ROWS & 31)) bulk_g2s(wave_s + FULL_ROWS * G::PITCH, src + FULL_ROWS * G::HOP, REM * 4, bar);
+    for (int row = warp; row < FULL_ROWS; row += G::NWK) bulk_g2s(wave_s + row * G::PITCH, src + row * G::HOP, G::HOP * 4, bar);
+    if (REM > 0 && warp == FULL_ROWS % G::NWK) bulk_g2s(wave_s + FULL_ROWS * G::PITCH, src + FULL_ROWS * G::HOP, REM * 4, bar);
+  }
+  __syncwarp();
 }
 
 template <class G, int NTHREADS>
@@ -154,7 +165,6 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
 
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const bool producer = warp == G::NW;
   const int group_id = blockIdx.x / a.group;
   const int rank = blockIdx.x - group_id * a.group;
   const float log_floor = a.log_floor, log_add = a.log_add, log_scale = a.log_scale;
@@ -165,13 +175,21 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
 
   // one-time setup: stage-1 constants into shared memory (the four column groups of a warp read
   // four different rows of the table at once), mbarrier for the TMA tile copies
-  for (int i = threadIdx.x; i < G::N2 * G::S1_STRIDE; i += NT) s1_s[i] = tab.s1[i];
+  if (!G::S1_CONST_REGS)
+    for (int i = threadIdx.x; i < G::N2 * G::S1_STRIDE; i += NT) s1_s[i] = tab.s1[i];
   if (threadIdx.x == 0) {
     mbar_init(&s_mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   unsigned parity = 0;
+  // N = 400: this warp's stage-1 constants, resident in registers for the whole kernel
+  float s1c[G::S1_CONST_REGS ? G::S1_STRIDE : 1];
+  if (G::S1_CONST_REGS && tab.s1_tasks[warp][0] >= 0)
+    stage1_consts<G>(tab.s1, tab.s1_tasks[warp][0], lane, reinterpret_cast<float(&)[G::S1_STRIDE]>(s1c));
+#ifdef LM_TIMELINE
+  int tl_tile = 0;
+#endif
 
   for (int clip = group_id; clip < a.batch; clip += a.n_groups) {
     const float* cptr = a.wave + (long long)clip * a.clip_stride;
@@ -182,114 +200,154 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
     const int t1 = (int)((long long)(rank + 1) * a.tiles_per_clip / a.group);
     const bool track = NORM && (t1 - t0 <= kMaxLocalTiles);
     float rmax = -INFINITY;
-    int staged = -1;          // tile whose waveform is in (or on its way into) wave_s
-    bool staged_tma = false;  // ... and whether it arrives through the mbarrier
+    bool staged_tma = false;  // the tile being staged into wave_s arrives through the mbarrier
 
     // CTA-uniform: start filling wave_s with the tile that begins at sample s
     auto fetch = [&](long long s) -> bool {
       const bool tma = a.tma_ok && tile_is_interior<G>(s, valid);
       if (tma) {
-        if (producer) load_tile_tma<G>(wave_s, cptr + s, &s_mbar, lane);
+        load_tile_tma<G>(wave_s, cptr + s, &s_mbar, warp, lane);
       } else {
         load_tile_edge<G, NT>(wave_s, cptr, s, a.n_samples, valid);
       }
       return tma;
     };
 
-    // Per computed tile: [stage 1] barrier [TMA prefetch | stage 2] barrier [mel].  The mel phase
-    // of tile t and stage 1 of the next tile share an interval, so uneven filter runs are absorbed.
+    auto tile_s0 = [&](int t) { return (long long)t * G::F * G::HOP - G::N / 2; };
+    auto next_loud = [&](int t) {            // first tile >= t that has to be computed
+      while (t < t1 && tile_is_silent<G>(tile_s0(t), a.n_samples, valid)) ++t;
+      return t;
+    };
+
+    // ---- silent tiles (all zero padding) are never computed
     for (int t = t0; t < t1; ++t) {
-      const int f0 = t * G::F;
-      const long long s0 = (long long)f0 * G::HOP - G::N / 2;
-      if (tile_is_silent<G>(s0, a.n_samples, valid)) {          // CTA-uniform
-        rmax = fmaxf(rmax, silent_val);
-        if (NORM) {
-          if (track && threadIdx.x == 0) s_silent[t - t0] = 1;
-        } else {
-          // no normalisation: the constant can be written right away
-          const int fend = min(f0 + G::F, a.n_frames);
-          for (int m = warp; m < a.n_mels; m += G::NWK)
-            for (int f = f0 + lane; f < fend; f += 32) oc[(long long)m * a.n_frames + f] = silent_val;
-        }
-        continue;
+      const bool silent = tile_is_silent<G>(tile_s0(t), a.n_samples, valid);       // CTA-uniform
+      if (NORM && track && threadIdx.x == 0) s_silent[t - t0] = silent ? 1 : 0;
+      if (!silent) continue;
+      rmax = fmaxf(rmax, silent_val);
+      if (!NORM) {                            // no normalisation: the constant can be written right away
+        const int f0 = t * G::F, fend = min(f0 + G::F, a.n_frames);
+        for (int m = warp; m < a.n_mels; m += G::NWK)
+          for (int f = f0 + lane; f < fend; f += 32) oc[(long long)m * a.n_frames + f] = silent_val;
       }
-      if (NORM && track && threadIdx.x == 0) s_silent[t - t0] = 0;
-      if (staged != t) {                                        // first tile of a run: fetch it now
-        staged_tma = fetch(s0);
-        if (!staged_tma) __syncthreads();
-      }
-      if (staged_tma) {                                         // the bulk copies have landed
+    }
+
+    auto wait_wave = [&]() __attribute__((always_inline)) {                  // the bulk copies of the staged tile have landed
+      if (staged_tma) {
         mbar_wait(&s_mbar, parity);
         parity ^= 1u;
       }
-      // ---- stage 1: S1_TASKS / NW tasks of (8 frame slots x 4 columns) per warp
-      if (!producer) {
+    };
+    auto do_s1 = [&]() __attribute__((always_inline)) {                      // stage 1: this warp's tasks of (8 frame slots x 4 columns)
 #pragma unroll 1
-        for (int task = warp; task < G::S1_TASKS; task += G::NW) stage1_task<G, T>(wave_s, Y, s1_s, task, lane);
+      for (int i = 0; i < G::S1_MAX; ++i) {
+        const int task = tab.s1_tasks[warp][i];
+        if (task < 0) break;
+        if (G::S1_CONST_REGS)
+          stage1_task_c<G, T>(wave_s, Y, reinterpret_cast<const float(&)[G::S1_STRIDE]>(s1c), task, lane);
+        else
+          stage1_task<G, T>(wave_s, Y, s1_s, task, lane);
       }
-      __syncthreads();
-      // ---- the waveform tile is dead: fetch the next one behind stage 2
-      const long long s1 = s0 + (long long)G::F * G::HOP;
-      const bool next_needed = (t + 1 < t1) && !tile_is_silent<G>(s1, a.n_samples, valid);
-      if (!ALIAS && next_needed) {
-        staged_tma = fetch(s1);
-        staged = t + 1;
+    };
+    auto do_mel = [&](int t) __attribute__((always_inline)) {                // mel projection, log, store, running max / tile min
+      const int f0 = t * G::F;
+      const int f = f0 + lane;
+      const bool full = f0 + G::F <= a.n_frames;            // CTA-uniform: only a clip's last tile is not
+      float* op = oc + (long long)tab.mel_begin[warp] * a.n_frames + f;
+      const long long ostep = a.n_frames;
+      float tmin = INFINITY;
+      if (full) {
+        mel_task<G, T>(P, tab, warp, lane, [&](T acc) {
+          T v = acc;
+          if (KIND == 1 || KIND == 3) v = vmuls(vlog2_clamp(v, log_floor), log_scale);
+          if (KIND == 2) v = vmuls(vlog2_add(v, log_add), log_scale);
+          if (NORM) {
+            rmax = vhmax(rmax, v);
+            tmin = vhmin(tmin, v);
+            v = vmulc(vadds(v, 4.0f), 0.25f);
+          }
+          op[0] = vlo(v);
+          if (G::PK == 2) op[32] = vhi(v);
+          op += ostep;
+        });
+      } else {
+        const bool ok0 = f < a.n_frames, ok1 = (G::PK == 2) && (f + 32 < a.n_frames);
+        mel_task<G, T>(P, tab, warp, lane, [&](T acc) {
+          T v = acc;
+          if (KIND == 1 || KIND == 3) v = vmuls(vlog2_clamp(v, log_floor), log_scale);
+          if (KIND == 2) v = vmuls(vlog2_add(v, log_add), log_scale);
+          if (NORM) {
+            if (ok0) { rmax = fmaxf(rmax, vlo(v)); tmin = fminf(tmin, vlo(v)); }
+            if (ok1) { rmax = fmaxf(rmax, vhi(v)); tmin = fminf(tmin, vhi(v)); }
+            v = vmulc(vadds(v, 4.0f), 0.25f);
+          }
+          if (ok0) op[0] = vlo(v);
+          if (ok1) op[32] = vhi(v);
+          op += ostep;
+        });
       }
-      // ---- stage 2: rows k1 = 1..H1-1 on warps 0..NW-2, the real row 0 on warp NW-1 and the
-      //      half row H1 on the producer warp (behind its copy instructions)
-      stage2_task<G, T>(Y, P, warp < G::NW - 1 ? warp + 1 : (producer ? G::H1 : 0), lane);
-      __syncthreads();
-      // ---- mel projection, log, store, running max / tile min (all NWK warps)
-      {
-        const int f = f0 + lane;
-        const bool full = f0 + G::F <= a.n_frames;            // CTA-uniform: only a clip's last tile is not
-        float* op = oc + (long long)tab.mel_begin[warp] * a.n_frames + f;
-        const long long ostep = a.n_frames;
-        float tmin = INFINITY;
-        if (full) {
-          mel_task<G, T>(P, tab, warp, lane, [&](T acc) {
-            T v = acc;
-            if (KIND == 1 || KIND == 3) v = vmuls(vlog2_clamp(v, log_floor), log_scale);
-            if (KIND == 2) v = vmuls(vlog2_add(v, log_add), log_scale);
-            if (NORM) {
-              rmax = vhmax(rmax, v);
-              tmin = vhmin(tmin, v);
-              v = vmulc(vadds(v, 4.0f), 0.25f);
-            }
-            op[0] = vlo(v);
-            if (G::PK == 2) op[32] = vhi(v);
-            op += ostep;
-          });
-        } else {
-          const bool ok0 = f < a.n_frames, ok1 = (G::PK == 2) && (f + 32 < a.n_frames);
-          mel_task<G, T>(P, tab, warp, lane, [&](T acc) {
-            T v = acc;
-            if (KIND == 1 || KIND == 3) v = vmuls(vlog2_clamp(v, log_floor), log_scale);
-            if (KIND == 2) v = vmuls(vlog2_add(v, log_add), log_scale);
-            if (NORM) {
-              if (ok0) { rmax = fmaxf(rmax, vlo(v)); tmin = fminf(tmin, vlo(v)); }
-              if (ok1) { rmax = fmaxf(rmax, vhi(v)); tmin = fminf(tmin, vhi(v)); }
-              v = vmulc(vadds(v, 4.0f), 0.25f);
-            }
-            if (ok0) op[0] = vlo(v);
-            if (ok1) op[32] = vhi(v);
-            op += ostep;
-          });
-        }
-        if (track) {
+      if (track) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-          if (lane == 0) s_tmin[t - t0][warp] = tmin;
-        }
+        for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        if (lane == 0) s_tmin[t - t0][warp] = tmin;
       }
-      if (ALIAS) {
+    };
+
+    // ---- computed tiles, software pipelined:
+    //   S1(t) | barrier | TMA prefetch(t') + S2(t) | barrier | { M(t), S1(t') in either order } | ...
+    // M(t) (shared-memory bound) and S1(t') (FP32-pipe bound) share an interval; one third of the
+    // warps runs them in the opposite order, so the two kinds of work overlap instead of all
+    // warps hitting the same pipe at the same time.
+    const bool s1_first = ((warp >> 2) & 1) != 0;
+    int t = next_loud(t0);
+    if (t < t1) {
+      staged_tma = fetch(tile_s0(t));
+      if (!staged_tma) __syncthreads();
+      wait_wave();
+      LM_STAMP(1)
+      do_s1();
+    }
+    while (t < t1) {
+      LM_STAMP(2)
+      __syncthreads();                                        // Y(t) complete, waveform tile dead
+      const int tn = next_loud(t + 1);
+      const bool pre = !ALIAS && tn < t1;
+      if (pre) staged_tma = fetch(tile_s0(tn));               // behind stage 2
+#pragma unroll 1
+      for (int i = 0; i < G::S2_MAX; ++i) {                   // stage 2: this warp's rows k1
+        const int k1 = tab.s2_rows[warp][i];
+        if (k1 < 0) break;
+        stage2_task<G, T>(Y, P, k1, lane);
+      }
+      LM_STAMP(4)
+      __syncthreads();                                        // P(t) complete
+      if (!ALIAS) {
+        if (s1_first && pre) {
+          wait_wave();
+          do_s1();
+          do_mel(t);
+        } else {
+          do_mel(t);
+          LM_STAMP(6)
+          if (pre) {
+            wait_wave();
+            do_s1();
+          }
+        }
+      } else {
+        do_mel(t);
         __syncthreads();   // P shares the waveform buffer: the next tile is fetched only now
-        if (next_needed) {
-          staged_tma = fetch(s1);
-          staged = t + 1;
+        if (tn < t1) {
+          staged_tma = fetch(tile_s0(tn));
           if (!staged_tma) __syncthreads();
+          wait_wave();
+          do_s1();
         }
       }
+#ifdef LM_TIMELINE
+      ++tl_tile;
+#endif
+      t = tn;
     }
 
     if (NORM) {

@@ -35,6 +35,50 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
       c[G::N1 + 2 * (k - 1) + 1] = (float)std::sin(ang);
     }
   }
+  // ---- stage-1 / stage-2 work tables, balanced per SM sub-partition (warp id mod 4)
+  {
+    std::memset(t.s1_tasks, -1, sizeof(t.s1_tasks));
+    std::memset(t.s2_rows, -1, sizeof(t.s2_rows));
+    std::vector<int> n1(G::NWK, 0), n2(G::NWK, 0);
+    std::vector<long> load(4, 0);
+    auto warp_of = [&](int part, const std::vector<int>& cnt, int cap) {   // least-busy warp of a partition
+      int best = -1;
+      for (int w = part; w < G::NWK; w += 4)
+        if (cnt[w] < cap && (best < 0 || cnt[w] < cnt[best])) best = w;
+      return best;
+    };
+    if (G::S1_CONST_REGS) {
+      // a warp's tasks share one column group (so its constants can stay in registers):
+      // the 4 frame octets of column group cg are split 2 + 2 over two warps
+      int w = 0;
+      for (int cg = 0; cg < G::CGROUPS; ++cg)
+        for (int half = 0; half < 2; ++half, ++w) {
+          if (w >= G::NWK) return "internal: stage-1 work table overflow";
+          for (int i = 0; i < 2; ++i) t.s1_tasks[w][n1[w]++] = (signed char)((2 * half + i) * G::CGROUPS + cg);
+        }
+    } else {
+      for (int task = 0; task < G::S1_TASKS; ++task) {     // equal-cost tasks: round robin over partitions
+        int part = task % 4;
+        int w = warp_of(part, n1, G::S1_MAX);
+        if (w < 0) return "internal: stage-1 work table overflow";
+        t.s1_tasks[w][n1[w]++] = (signed char)task;
+      }
+    }
+    // rows by decreasing cost: general rows, then the half row k1 = H1, then the real row k1 = 0
+    std::vector<std::pair<int, int>> rows;                  // (cost, k1)
+    for (int k = 1; k < G::H1; ++k) rows.push_back({100, k});
+    rows.push_back({77, G::H1});
+    rows.push_back({44, 0});
+    for (auto& r : rows) {
+      int part = 0;
+      for (int q = 1; q < 4; ++q)
+        if (load[q] < load[part]) part = q;
+      int w = warp_of(part, n2, G::S2_MAX);
+      if (w < 0) return "internal: stage-2 work table overflow";
+      t.s2_rows[w][n2[w]++] = (signed char)r.second;
+      load[part] += r.first;
+    }
+  }
   // ---- banded supports
   std::vector<int> lo(n_mels, 0), cnt(n_mels, 0);
   for (int m = 0; m < n_mels; ++m) {

@@ -53,13 +53,14 @@ int run(const float* wave, long batch, long stride, const int32_t* lengths, int 
       const long s0 = (long)f0 * G::HOP - G::N / 2;
       for (int r = 0; r < G::SPAN; ++r)
         wave_s[wave_index<G>(r)] = load_sample(clip, s0 + r, n_samples, valid);
-      for (int w = 0; w < G::NW; ++w)
-        for (int task = w; task < G::S1_TASKS; task += G::NW)
+      for (int w = 0; w < G::NWK; ++w)
+        for (int i = 0; i < G::S1_MAX && tab.s1_tasks[w][i] >= 0; ++i)
           for (int lane = 0; lane < 32; ++lane)
-            stage1_task<G, T>(wave_s.data(), Y.data(), tab.s1, task, lane);
-      for (int w = 0; w < G::NWK; ++w)       // warp w < NW-1: row w+1; warp NW-1: row 0; producer: row H1
-        for (int lane = 0; lane < 32; ++lane)
-          stage2_task<G, T>(Y.data(), P.data(), w < G::NW - 1 ? w + 1 : (w == G::NW - 1 ? 0 : G::H1), lane);
+            stage1_task<G, T>(wave_s.data(), Y.data(), tab.s1, tab.s1_tasks[w][i], lane);
+      for (int w = 0; w < G::NWK; ++w)
+        for (int i = 0; i < G::S2_MAX && tab.s2_rows[w][i] >= 0; ++i)
+          for (int lane = 0; lane < 32; ++lane)
+            stage2_task<G, T>(Y.data(), P.data(), tab.s2_rows[w][i], lane);
       for (int w = 0; w < G::NWK; ++w)
         for (int lane = 0; lane < 32; ++lane) {
           int m = tab.mel_begin[w];
