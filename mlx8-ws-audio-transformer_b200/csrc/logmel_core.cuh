@@ -89,6 +89,17 @@ struct alignas(16) Tables {
   unsigned short mel_begin[G::NWK + 1];
   unsigned short mel_ng[G::NWK];
   unsigned short mel_woff[G::NWK];       // in units of 4 weights
+  // Scan form of the mel projection (mel_scan != 0; triangular banks, where every bin feeds at
+  // most two ADJACENT filters a(k), a(k)+1 and a(k) never decreases): melw then holds one weight
+  // pair per bin, melw[2k] for filter a(k) and melw[2k+1] for a(k)+1.  Warp w walks the bins from
+  // scan_bin0[w] on, segment by segment (segment = the bins sharing one a(k)); scan_n lists the
+  // segment lengths from scan_soff[w] on: one lead-in segment (a = mel_begin[w] - 1, its first
+  // weights belong to the previous warp's last filter) and one per filter of the run.  Every
+  // power value is then read from shared memory once per warp instead of once per filter.
+  unsigned short scan_bin0[G::NWK];
+  unsigned short scan_soff[G::NWK];
+  unsigned char scan_n[kMaxMels + 2 * G::NWK];
+  unsigned char mel_scan;
   signed char s1_tasks[G::NWK][G::S1_MAX];   // stage-1 tasks of each warp (-1: none)
   signed char s2_rows[G::NWK][G::S2_MAX];    // stage-2 rows k1 of each warp (-1: none)
 };
@@ -183,21 +194,23 @@ LM_HD void stage1_consts(const float* __restrict__ s1tab, int task, int lane, fl
 }
 
 template <class G, typename T>
-LM_HD void stage1_task_c(const float* __restrict__ wave_s, T* __restrict__ Y,
-                         const float (&cst)[G::S1_STRIDE], int task, int lane) {
-  constexpr int N1 = G::N1, N2 = G::N2, H1 = G::H1;
-  const int cg = task % G::CGROUPS, fg = task / G::CGROUPS;
-  const int b = 4 * cg + (lane >> 3);
-  const int p = 8 * fg + (lane & 7);
+LM_HD void stage1_load(const float* __restrict__ wave_s, int task, int lane, T (&x)[G::N1]) {
+  const int b = 4 * (task % G::CGROUPS) + (lane >> 3);
+  const int p = 8 * (task / G::CGROUPS) + (lane & 7);
   const float* src = wave_s + p * G::PITCH + b;
-  T x[N1];
+#pragma unroll
+  for (int a = 0; a < G::N1; ++a)   // sample n = N2*a + b of frame p: r = HOP*p + n, and n / HOP == (N2*a) / HOP
+    x[a] = VT<T>::load_wave(src + (G::N2 * a + 4 * ((G::N2 * a) / G::HOP)), 32 * G::PITCH);
+}
+
+template <class G, typename T>
+LM_HD void stage1_compute(const T (&x)[G::N1], T* __restrict__ Y, const float (&cst)[G::S1_STRIDE], int task, int lane) {
+  constexpr int N1 = G::N1, N2 = G::N2, H1 = G::H1;
+  const int b = 4 * (task % G::CGROUPS) + (lane >> 3);
+  const int p = 8 * (task / G::CGROUPS) + (lane & 7);
   float w[N1], tr[H1 + 1], ti[H1 + 1];
 #pragma unroll
-  for (int a = 0; a < N1; ++a) {
-    // sample n = N2*a + b of frame p: r = HOP*p + n, and n / HOP == (N2*a) / HOP
-    x[a] = VT<T>::load_wave(src + (N2 * a + 4 * ((N2 * a) / G::HOP)), 32 * G::PITCH);
-    w[a] = cst[a];
-  }
+  for (int a = 0; a < N1; ++a) w[a] = cst[a];
   tr[0] = 1.0f;
   ti[0] = 0.0f;
 #pragma unroll
@@ -213,6 +226,26 @@ LM_HD void stage1_task_c(const float* __restrict__ wave_s, T* __restrict__ Y,
   for (int k = 0; k <= H1; ++k) dre[k * N2 * 32] = yr[k];
 #pragma unroll
   for (int k = 1; k <= H1; ++k) dim[(k - 1) * N2 * 32] = yi[k];
+}
+
+template <class G, typename T>
+LM_HD void stage1_task_c(const float* __restrict__ wave_s, T* __restrict__ Y,
+                         const float (&cst)[G::S1_STRIDE], int task, int lane) {
+  T x[G::N1];
+  stage1_load<G, T>(wave_s, task, lane, x);
+  stage1_compute<G, T>(x, Y, cst, task, lane);
+}
+
+// two tasks of one warp: the second task's samples are fetched before the first task's
+// arithmetic starts, so the shared-memory latency and the FP32 work overlap
+template <class G, typename T>
+LM_HD void stage1_task_pair(const float* __restrict__ wave_s, T* __restrict__ Y,
+                            const float (&cst)[G::S1_STRIDE], int ta, int tb, int lane) {
+  T xa[G::N1], xb[G::N1];
+  stage1_load<G, T>(wave_s, ta, lane, xa);
+  stage1_load<G, T>(wave_s, tb, lane, xb);
+  stage1_compute<G, T>(xa, Y, cst, ta, lane);
+  stage1_compute<G, T>(xb, Y, cst, tb, lane);
 }
 
 template <class G, typename T>
@@ -334,7 +367,35 @@ LM_HD void mel_run(const T* __restrict__ P, const Tables<G>& tab, int m0, int m1
 }
 
 template <class G, typename T, class Emit>
+LM_HD void mel_task_scan(const T* __restrict__ P, const Tables<G>& tab, int w, int lane, Emit&& emit) {
+  const int nseg = tab.mel_begin[w + 1] - tab.mel_begin[w] + 1;
+  const unsigned char* cnt = tab.scan_n + tab.scan_soff[w];
+  const T* src = P + tab.scan_bin0[w] * 32 + lane;
+  const float* wp = tab.melw + 2 * tab.scan_bin0[w];
+  T acc0 = vzero<T>(), acc1 = vzero<T>();
+#pragma unroll 1
+  for (int sg = 0; sg < nseg; ++sg) {
+    const int n = cnt[sg];
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      const T p = src[0];
+      acc0 = vfmas(p, wp[0], acc0);
+      acc1 = vfmas(p, wp[1], acc1);
+      src += 32;
+      wp += 2;
+    }
+    if (sg > 0) emit(acc0);
+    acc0 = acc1;
+    acc1 = vzero<T>();
+  }
+}
+
+template <class G, typename T, class Emit>
 LM_HD void mel_task(const T* __restrict__ P, const Tables<G>& tab, int w, int lane, Emit&& emit) {
+  if (tab.mel_scan) {
+    mel_task_scan<G, T>(P, tab, w, lane, emit);
+    return;
+  }
   const int m0 = tab.mel_begin[w], m1 = tab.mel_begin[w + 1];
   const int ng = tab.mel_ng[w], woff = tab.mel_woff[w];
   switch (ng) {      // warp-uniform

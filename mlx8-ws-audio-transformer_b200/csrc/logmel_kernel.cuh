@@ -36,8 +36,12 @@ struct KArgs {
 #define LM_STAMP(slot)                                                                         \
   if (a.timeline && blockIdx.x == 0 && lane == 0 && tl_tile < 48)                              \
     a.timeline[(tl_tile * 16 + warp) * 8 + (slot)] = clock64();
+#define LM_CSTAMP(slot)                                                                        \
+  if (a.timeline && blockIdx.x == 0 && threadIdx.x == 0 && tl_clip < 16)                       \
+    a.timeline[48 * 16 * 8 + tl_clip * 8 + (slot)] = clock64();
 #else
 #define LM_STAMP(slot)
+#define LM_CSTAMP(slot)
 #endif
 
 template <class G>
@@ -88,41 +92,64 @@ __device__ __forceinline__ void bulk_g2s(float* dst_smem, const float* src, unsi
                : "memory");
 }
 
-// Stage the SPAN samples of a tile into shared memory (wave_index layout).
+// Stage the SPAN samples of a tile into shared memory (wave_index layout), row by row.
 //
-// Interior tiles: ONE thread issues one TMA bulk copy per hop row (HOP*4 bytes, both addresses
-// 16-byte aligned) onto an mbarrier; no other thread spends an instruction on the waveform.
-// Tiles that touch a clip edge or the zero padding (and unaligned inputs) are filled by all
-// threads through load_sample (reflection / zero fill).
+// A row (HOP samples, the last one shorter) that lies inside the clip's audio is fetched with
+// ONE TMA bulk copy (both addresses 16-byte aligned) onto the mbarrier; lane 0 of warp w issues
+// the copies of rows w, w + NWK, ... (UBLKCP takes warp-uniform operands, so spreading rows over
+// warps -- not lanes -- is what issues them in parallel).  Rows that touch a clip edge or the
+// zero padding (at most a handful per clip), and every row of an unaligned input, are filled by
+// their warp through load_sample (reflection / zero fill).
+// Returns bit 0: some rows arrive through the mbarrier, bit 1: some rows were stored by threads.
 template <class G>
-__device__ __forceinline__ bool tile_is_interior(long long s0, int valid) {
-  return (s0 >= 0) && (s0 + G::SPAN <= (long long)valid);
-}
-
-// Called by every warp of the CTA: lane 0 of warp w issues the bulk copies of rows w, w + NWK,
-// ... (UBLKCP takes warp-uniform operands, so spreading rows over warps -- not lanes -- is what
-// issues them in parallel); warp 0 arms the mbarrier with the tile's byte count.
-template <class G>
-__device__ __forceinline__ void load_tile_tma(float* wave_s, const float* __restrict__ src, unsigned long long* bar,
-                                              int warp, int lane) {
+__device__ __forceinline__ int load_tile(float* wave_s, const float* __restrict__ clip, long long s0, int n_samples,
+                                         int valid, bool tma_ok, unsigned long long* bar, int warp, int lane) {
   constexpr int FULL_ROWS = G::SPAN / G::HOP;
   constexpr int REM = G::SPAN - FULL_ROWS * G::HOP;
+  constexpr int ROWS = FULL_ROWS + (REM > 0 ? 1 : 0);
   static_assert((G::HOP * 4) % 16 == 0 && (REM * 4) % 16 == 0 && (G::PITCH * 4) % 16 == 0, "bulk copies move 16-byte units");
-  if (lane == 0) {
+  // interior rows form the contiguous range [r_lo, r_hi)   (CTA-uniform)
+  int r_lo = 0, r_hi = 0;
+  if (tma_ok) {
+    r_lo = s0 >= 0 ? 0 : (int)((-s0 + G::HOP - 1) / G::HOP);
+    const long long room = (long long)valid - s0;              // samples of audio from s0 on
+    r_hi = room <= 0 ? 0 : (int)min((long long)FULL_ROWS, room / G::HOP);
+    if (REM > 0 && r_hi == FULL_ROWS && room >= G::SPAN) r_hi = ROWS;
+    if (r_lo > r_hi) r_lo = r_hi;
+  }
+  const int n_tma = r_hi - r_lo;
+  if (n_tma > 0 && lane == 0) {
     fence_proxy_async();    // earlier generic-proxy reads of this buffer are ordered before the async writes
-    if (warp == 0) mbar_expect_tx(bar, (unsigned)G::SPAN * 4u);
+    if (warp == 0) {
+      const unsigned bytes = (unsigned)(min(r_hi, FULL_ROWS) - r_lo) * (G::HOP * 4u) + (r_hi == ROWS && REM > 0 ? REM * 4u : 0u);
+      mbar_expect_tx(bar, bytes);
+    }
+  }
+  if (n_tma == ROWS) {
+    // common case, every row is interior: lane 0 walks this warp's rows with two running pointers
+    if (lane == 0) {
+      float* dst = wave_s + warp * G::PITCH;
+      const float* src = clip + s0 + warp * G::HOP;
 #pragma unroll 1
-    for (int row = warp; row < FULL_ROWS; row += G::NWK) bulk_g2s(wave_s + row * G::PITCH, src + row * G::HOP, G::HOP * 4, bar);
-    if (REM > 0 && warp == FULL_ROWS % G::NWK) bulk_g2s(wave_s + FULL_ROWS * G::PITCH, src + FULL_ROWS * G::HOP, REM * 4, bar);
+      for (int row = warp; row < FULL_ROWS; row += G::NWK, dst += G::NWK * G::PITCH, src += G::NWK * G::HOP)
+        bulk_g2s(dst, src, G::HOP * 4, bar);
+      if (REM > 0 && warp == FULL_ROWS % G::NWK)
+        bulk_g2s(wave_s + FULL_ROWS * G::PITCH, clip + s0 + FULL_ROWS * G::HOP, REM * 4, bar);
+    }
+  } else {
+#pragma unroll 1
+    for (int row = warp; row < ROWS; row += G::NWK) {
+      const int len = (row < FULL_ROWS) ? G::HOP : REM;
+      if (row >= r_lo && row < r_hi) {
+        if (lane == 0) bulk_g2s(wave_s + row * G::PITCH, clip + s0 + (long long)row * G::HOP, len * 4, bar);
+      } else {
+        for (int i = lane; i < len; i += 32)
+          wave_s[row * G::PITCH + i] = load_sample(clip, (long)(s0 + (long long)row * G::HOP + i), n_samples, valid);
+      }
+    }
   }
   __syncwarp();
-}
-
-template <class G, int NTHREADS>
-__device__ __forceinline__ void load_tile_edge(float* wave_s, const float* __restrict__ clip, long long s0,
-                                               int n_samples, int valid) {
-  for (int r = threadIdx.x; r < G::SPAN; r += NTHREADS)
-    wave_s[wave_index<G>(r)] = load_sample(clip, (long)(s0 + r), n_samples, valid);
+  return (n_tma > 0 ? 1 : 0) | (n_tma < ROWS ? 2 : 0);
 }
 
 // every sample the tile touches (after reflection about the padded length) is zero padding
@@ -188,7 +215,7 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
   if (G::S1_CONST_REGS && tab.s1_tasks[warp][0] >= 0)
     stage1_consts<G>(tab.s1, tab.s1_tasks[warp][0], lane, reinterpret_cast<float(&)[G::S1_STRIDE]>(s1c));
 #ifdef LM_TIMELINE
-  int tl_tile = 0;
+  int tl_tile = 0, tl_clip = 0;
 #endif
 
   for (int clip = group_id; clip < a.batch; clip += a.n_groups) {
@@ -200,17 +227,15 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
     const int t1 = (int)((long long)(rank + 1) * a.tiles_per_clip / a.group);
     const bool track = NORM && (t1 - t0 <= kMaxLocalTiles);
     float rmax = -INFINITY;
+    LM_CSTAMP(0)
     bool staged_tma = false;  // the tile being staged into wave_s arrives through the mbarrier
 
-    // CTA-uniform: start filling wave_s with the tile that begins at sample s
+    // CTA-uniform: start filling wave_s with the tile that begins at sample s; returns whether
+    // some rows were written by threads (then a CTA barrier must precede their use)
     auto fetch = [&](long long s) -> bool {
-      const bool tma = a.tma_ok && tile_is_interior<G>(s, valid);
-      if (tma) {
-        load_tile_tma<G>(wave_s, cptr + s, &s_mbar, warp, lane);
-      } else {
-        load_tile_edge<G, NT>(wave_s, cptr, s, a.n_samples, valid);
-      }
-      return tma;
+      const int how = load_tile<G>(wave_s, cptr, s, a.n_samples, valid, a.tma_ok != 0, &s_mbar, warp, lane);
+      staged_tma = (how & 1) != 0;
+      return (how & 2) != 0;
     };
 
     auto tile_s0 = [&](int t) { return (long long)t * G::F * G::HOP - G::N / 2; };
@@ -239,14 +264,19 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
       }
     };
     auto do_s1 = [&]() __attribute__((always_inline)) {                      // stage 1: this warp's tasks of (8 frame slots x 4 columns)
+      if (G::S1_CONST_REGS) {
+        // exactly 0 or 2 tasks per warp, one straight-line block: the second task's shared-memory
+        // loads can be scheduled under the first task's arithmetic
+        const int ta = tab.s1_tasks[warp][0], tb = tab.s1_tasks[warp][1];
+        if (ta >= 0)
+          stage1_task_pair<G, T>(wave_s, Y, reinterpret_cast<const float(&)[G::S1_STRIDE]>(s1c), ta, tb, lane);
+      } else {
 #pragma unroll 1
-      for (int i = 0; i < G::S1_MAX; ++i) {
-        const int task = tab.s1_tasks[warp][i];
-        if (task < 0) break;
-        if (G::S1_CONST_REGS)
-          stage1_task_c<G, T>(wave_s, Y, reinterpret_cast<const float(&)[G::S1_STRIDE]>(s1c), task, lane);
-        else
+        for (int i = 0; i < G::S1_MAX; ++i) {
+          const int task = tab.s1_tasks[warp][i];
+          if (task < 0) break;
           stage1_task<G, T>(wave_s, Y, s1_s, task, lane);
+        }
       }
     };
     auto do_mel = [&](int t) __attribute__((always_inline)) {                // mel projection, log, store, running max / tile min
@@ -301,8 +331,7 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
     const bool s1_first = ((warp >> 2) & 1) != 0;
     int t = next_loud(t0);
     if (t < t1) {
-      staged_tma = fetch(tile_s0(t));
-      if (!staged_tma) __syncthreads();
+      if (fetch(tile_s0(t))) __syncthreads();
       wait_wave();
       LM_STAMP(1)
       do_s1();
@@ -312,7 +341,7 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
       __syncthreads();                                        // Y(t) complete, waveform tile dead
       const int tn = next_loud(t + 1);
       const bool pre = !ALIAS && tn < t1;
-      if (pre) staged_tma = fetch(tile_s0(tn));               // behind stage 2
+      if (pre) fetch(tile_s0(tn));                            // behind stage 2; the barrier below covers thread-written rows
 #pragma unroll 1
       for (int i = 0; i < G::S2_MAX; ++i) {                   // stage 2: this warp's rows k1
         const int k1 = tab.s2_rows[warp][i];
@@ -338,8 +367,7 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
         do_mel(t);
         __syncthreads();   // P shares the waveform buffer: the next tile is fetched only now
         if (tn < t1) {
-          staged_tma = fetch(tile_s0(tn));
-          if (!staged_tma) __syncthreads();
+          if (fetch(tile_s0(tn))) __syncthreads();
           wait_wave();
           do_s1();
         }
@@ -350,6 +378,7 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
       t = tn;
     }
 
+    LM_CSTAMP(1)
     if (NORM) {
       // ---- clip maximum: warp shuffle -> CTA -> clip group (release/acquire counter)
 #pragma unroll
@@ -371,6 +400,7 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
         s_max = m;
       }
       __syncthreads();
+      LM_CSTAMP(2)
       // ---- revisit only what the clamp actually touches
       const float thr = s_max - 8.0f;
       const float cval = (thr + 4.0f) * 0.25f;
@@ -415,7 +445,11 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
         }
       }
       __syncthreads();   // s_red / s_max / s_tmin are reused by the next clip
+      LM_CSTAMP(3)
     }
+#ifdef LM_TIMELINE
+    ++tl_clip;
+#endif
   }
 }
 

@@ -93,10 +93,35 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
       cnt[m] = last - first + 1;
     }
   }
-  // ---- contiguous runs of filters per warp, balanced on (groups of 4 weights) + epilogue cost
+  // ---- scan form: possible when every bin feeds at most two adjacent filters, in order
+  std::vector<int> a_of(G::NBINS, 0);
+  bool scan_ok = true;
+  {
+    int prev = 0;
+    for (int k = 0; k < G::NBINS && scan_ok; ++k) {
+      int first = -1, last = -1;
+      for (int m = 0; m < n_mels; ++m)
+        if (fbank[(size_t)k * n_mels + m] != 0.0f) {
+          if (first < 0) first = m;
+          last = m;
+        }
+      if (first < 0) {
+        a_of[k] = prev;
+      } else {
+        if (last - first > 1 || first < prev) scan_ok = false;
+        a_of[k] = first;
+        prev = first;
+      }
+    }
+  }
+  std::vector<int> nbin_of(n_mels + 1, 0);           // bins with a(k) == m
+  if (scan_ok)
+    for (int k = 0; k < G::NBINS; ++k) nbin_of[a_of[k]]++;
+  // ---- contiguous runs of filters per warp, balanced on their cost
   std::vector<long> cost(n_mels);
   long total = 0;
-  for (int m = 0; m < n_mels; ++m) total += (cost[m] = 9L * std::max(1, (cnt[m] + 3) / 4) + 14);
+  for (int m = 0; m < n_mels; ++m)
+    total += (cost[m] = scan_ok ? 7L * nbin_of[m] + 19 : 9L * std::max(1, (cnt[m] + 3) / 4) + 14);
   {
     int m = 0;
     long acc = 0;
@@ -108,7 +133,32 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
     }
     t.mel_begin[G::NWK] = (unsigned short)n_mels;
   }
-  // ---- grouped, zero padded weights; a run uses the group count of its widest filter
+  if (scan_ok) {
+    t.mel_scan = 1;
+    for (int k = 0; k < G::NBINS; ++k) {
+      const int a = a_of[k];
+      t.melw[2 * k] = fbank[(size_t)k * n_mels + a];
+      t.melw[2 * k + 1] = (a + 1 < n_mels) ? fbank[(size_t)k * n_mels + a + 1] : 0.0f;
+    }
+    int soff = 0;
+    for (int w = 0; w < G::NWK; ++w) {
+      const int m0 = t.mel_begin[w], m1 = t.mel_begin[w + 1];
+      // bins with a(k) in [m0 - 1, m1 - 1] are contiguous because a(k) never decreases
+      int k0 = 0;
+      while (k0 < G::NBINS && a_of[k0] < m0 - 1) ++k0;
+      t.scan_bin0[w] = (unsigned short)std::min(k0, G::NBINS - 1);
+      t.scan_soff[w] = (unsigned short)soff;
+      for (int cur = m0 - 1; cur <= m1 - 1; ++cur) {
+        int n = 0;
+        if (m1 > m0 && cur >= 0)
+          for (int k = 0; k < G::NBINS; ++k) n += (a_of[k] == cur);
+        if (n > 255) return "filter bank: a filter segment has more than 255 bins";
+        t.scan_n[soff++] = (unsigned char)n;
+      }
+    }
+    return std::string();
+  }
+  // ---- gather form: grouped, zero padded weights; a run uses the group count of its widest filter
   int off = 0;
   for (int w = 0; w < G::NWK; ++w) {
     const int m0 = t.mel_begin[w], m1 = t.mel_begin[w + 1];
