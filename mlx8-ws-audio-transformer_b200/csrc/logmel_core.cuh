@@ -42,7 +42,7 @@ struct Geo {
   static constexpr int NBINS = N / 2 + 1;
   // Warps per CTA: a multiple of 4 so that every SM sub-partition (warp id mod 4) holds the
   // same number of warps; the work tables below balance tasks per sub-partition.
-  static constexpr int NWK = (NFFT == 400) ? 11 : 16;
+  static constexpr int NWK = (NFFT == 400) ? 12 : 16;
   // N = 400: a warp's stage-1 tasks all use the same four columns, so their window samples and
   // twiddles (S1_STRIDE floats per lane) are loaded once per kernel and stay in registers; the
   // alternative -- fetching them from shared memory per task -- costs as many LSU wavefronts as

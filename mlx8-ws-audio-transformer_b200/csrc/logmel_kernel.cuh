@@ -265,11 +265,13 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
     };
     auto do_s1 = [&]() __attribute__((always_inline)) {                      // stage 1: this warp's tasks of (8 frame slots x 4 columns)
       if (G::S1_CONST_REGS) {
-        // exactly 0 or 2 tasks per warp, one straight-line block: the second task's shared-memory
-        // loads can be scheduled under the first task's arithmetic
+        // 0, 1 or 2 tasks per warp; a pair is one straight-line block in which the second task's
+        // samples are fetched before the first task's arithmetic starts
         const int ta = tab.s1_tasks[warp][0], tb = tab.s1_tasks[warp][1];
-        if (ta >= 0)
+        if (tb >= 0)
           stage1_task_pair<G, T>(wave_s, Y, reinterpret_cast<const float(&)[G::S1_STRIDE]>(s1c), ta, tb, lane);
+        else if (ta >= 0)
+          stage1_task_c<G, T>(wave_s, Y, reinterpret_cast<const float(&)[G::S1_STRIDE]>(s1c), ta, lane);
       } else {
 #pragma unroll 1
         for (int i = 0; i < G::S1_MAX; ++i) {

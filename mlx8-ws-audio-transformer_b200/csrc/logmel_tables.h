@@ -48,14 +48,28 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
       return best;
     };
     if (G::S1_CONST_REGS) {
-      // a warp's tasks share one column group (so its constants can stay in registers):
-      // the 4 frame octets of column group cg are split 2 + 2 over two warps
+      // a warp's tasks share one column group (so its constants can stay in registers): the 4
+      // frame octets of column group cg go to two warps, 2 + 2 ...
       int w = 0;
       for (int cg = 0; cg < G::CGROUPS; ++cg)
         for (int half = 0; half < 2; ++half, ++w) {
           if (w >= G::NWK) return "internal: stage-1 work table overflow";
           for (int i = 0; i < 2; ++i) t.s1_tasks[w][n1[w]++] = (signed char)((2 * half + i) * G::CGROUPS + cg);
         }
+      // ... then warps that are still idle take one task from the busiest sub-partition until
+      // every sub-partition (warp id mod 4) carries the same number of tasks
+      for (int idle = w; idle < G::NWK; ++idle) {
+        int load[4] = {0, 0, 0, 0};
+        for (int q = 0; q < G::NWK; ++q) load[q % 4] += n1[q];
+        int donor = -1;
+        for (int q = 0; q < idle; ++q)
+          if (n1[q] == 2 && q % 4 != idle % 4 && load[q % 4] > load[idle % 4] + 1 &&
+              (donor < 0 || load[q % 4] > load[donor % 4] || (load[q % 4] == load[donor % 4] && q > donor)))
+            donor = q;
+        if (donor < 0) break;
+        t.s1_tasks[idle][n1[idle]++] = t.s1_tasks[donor][--n1[donor]];
+        t.s1_tasks[donor][n1[donor]] = -1;
+      }
     } else {
       for (int task = 0; task < G::S1_TASKS; ++task) {     // equal-cost tasks: round robin over partitions
         int part = task % 4;
