@@ -26,6 +26,7 @@ enum : int { LOG_NONE = 0, LOG10_CLAMP_WHISPER_NORM = 1, LN_PLUS_EPS = 2, LOG10_
 
 constexpr int kMaxMels = 128;
 constexpr int kMaxMelWeights = 3072;
+constexpr int kMaxScanSteps = 1280;
 
 // ---------------------------------------------------------------------------------------
 // compile-time geometry
@@ -91,17 +92,23 @@ struct alignas(16) Tables {
   unsigned short mel_woff[G::NWK];       // in units of 4 weights
   // Scan form of the mel projection (mel_scan != 0; triangular banks, where every bin feeds at
   // most two ADJACENT filters a(k), a(k)+1 and a(k) never decreases): melw then holds one weight
-  // pair per bin, melw[2k] for filter a(k) and melw[2k+1] for a(k)+1.  Warp w walks the bins from
-  // scan_bin0[w] on, segment by segment (segment = the bins sharing one a(k)); scan_n lists the
-  // segment lengths from scan_soff[w] on: one lead-in segment (a = mel_begin[w] - 1, its first
-  // weights belong to the previous warp's last filter) and one per filter of the run.  Every
-  // power value is then read from shared memory once per warp instead of once per filter.
+  // pair per bin, melw[2k] for filter a(k) and melw[2k+1] for a(k)+1.  Warp w walks scan_nb[w]
+  // consecutive bins from scan_bin0[w] on with two running sums (acc0: filter a, acc1: filter
+  // a+1); scan_code (from scan_soff[w] on, one byte per bin) says what happens AFTER a bin:
+  //   bit 0  first shift:  filter a is complete -> emit acc0 (unless bit 2), acc0 = acc1, acc1 = 0
+  //   bit 1  second shift: a(k) jumps by two, filter a+1 has no bin of its own -> emit acc0
+  //          (unless bit 3), acc0 = 0
+  //   bit 2 / bit 3  the shifted-out filter belongs to the previous warp (lead-in): no emit
+  // Every power value is read from shared memory once per warp instead of once per filter, and
+  // the walk is one flat loop (no per-filter inner loops).
   unsigned short scan_bin0[G::NWK];
-  unsigned short scan_soff[G::NWK];
-  unsigned char scan_n[kMaxMels + 2 * G::NWK];
+  unsigned short scan_soff[G::NWK];         // multiple of 4
+  unsigned short scan_nb[G::NWK];
+  alignas(4) unsigned char scan_code[kMaxScanSteps];   // read four codes at a time
   unsigned char mel_scan;
   signed char s1_tasks[G::NWK][G::S1_MAX];   // stage-1 tasks of each warp (-1: none)
   signed char s2_rows[G::NWK][G::S2_MAX];    // stage-2 rows k1 of each warp (-1: none)
+  signed char loader_warp;                   // a warp without stage-2 rows issues the tile's TMA copies (-1: none)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -368,25 +375,46 @@ LM_HD void mel_run(const T* __restrict__ P, const Tables<G>& tab, int m0, int m1
 
 template <class G, typename T, class Emit>
 LM_HD void mel_task_scan(const T* __restrict__ P, const Tables<G>& tab, int w, int lane, Emit&& emit) {
-  const int nseg = tab.mel_begin[w + 1] - tab.mel_begin[w] + 1;
-  const unsigned char* cnt = tab.scan_n + tab.scan_soff[w];
+  const int nb = tab.scan_nb[w];
+  const unsigned char* code = tab.scan_code + tab.scan_soff[w];
   const T* src = P + tab.scan_bin0[w] * 32 + lane;
   const float* wp = tab.melw + 2 * tab.scan_bin0[w];
   T acc0 = vzero<T>(), acc1 = vzero<T>();
-#pragma unroll 1
-  for (int sg = 0; sg < nseg; ++sg) {
-    const int n = cnt[sg];
-#pragma unroll 1
-    for (int i = 0; i < n; ++i) {
-      const T p = src[0];
-      acc0 = vfmas(p, wp[0], acc0);
-      acc1 = vfmas(p, wp[1], acc1);
-      src += 32;
-      wp += 2;
-    }
-    if (sg > 0) emit(acc0);
+  // what follows a bin whose code is non-zero (warp-uniform branches)
+  auto shift = [&](unsigned c) {
+    if (!(c & 4u)) emit(acc0);
     acc0 = acc1;
     acc1 = vzero<T>();
+    if (c & 2u) {
+      if (!(c & 8u)) emit(acc0);
+      acc0 = vzero<T>();
+    }
+  };
+  int i = 0;
+#pragma unroll 1
+  for (; i + 4 <= nb; i += 4, src += 4 * 32, wp += 8) {
+    const T p0 = src[0], p1 = src[32], p2 = src[64], p3 = src[96];
+    const unsigned c4 = *reinterpret_cast<const unsigned*>(code + i);
+    acc0 = vfmas(p0, wp[0], acc0);
+    acc1 = vfmas(p0, wp[1], acc1);
+    if (c4 & 0x000000ffu) shift(c4);
+    acc0 = vfmas(p1, wp[2], acc0);
+    acc1 = vfmas(p1, wp[3], acc1);
+    if (c4 & 0x0000ff00u) shift(c4 >> 8);
+    acc0 = vfmas(p2, wp[4], acc0);
+    acc1 = vfmas(p2, wp[5], acc1);
+    if (c4 & 0x00ff0000u) shift(c4 >> 16);
+    acc0 = vfmas(p3, wp[6], acc0);
+    acc1 = vfmas(p3, wp[7], acc1);
+    if (c4 & 0xff000000u) shift(c4 >> 24);
+  }
+#pragma unroll 1
+  for (; i < nb; ++i, src += 32, wp += 2) {
+    const T p0 = src[0];
+    const unsigned c = code[i];
+    acc0 = vfmas(p0, wp[0], acc0);
+    acc1 = vfmas(p0, wp[1], acc1);
+    if (c) shift(c);
   }
 }
 

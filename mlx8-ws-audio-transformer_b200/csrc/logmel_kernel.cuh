@@ -85,6 +85,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one lane of a converged warp (lets ptxas keep the bulk-copy operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void bulk_g2s(float* dst_smem, const float* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst_smem)),
@@ -95,15 +107,18 @@ __device__ __forceinline__ void bulk_g2s(float* dst_smem, const float* src, unsi
 // Stage the SPAN samples of a tile into shared memory (wave_index layout), row by row.
 //
 // A row (HOP samples, the last one shorter) that lies inside the clip's audio is fetched with
-// ONE TMA bulk copy (both addresses 16-byte aligned) onto the mbarrier; lane 0 of warp w issues
-// the copies of rows w, w + NWK, ... (UBLKCP takes warp-uniform operands, so spreading rows over
-// warps -- not lanes -- is what issues them in parallel).  Rows that touch a clip edge or the
-// zero padding (at most a handful per clip), and every row of an unaligned input, are filled by
-// their warp through load_sample (reflection / zero fill).
+// ONE TMA bulk copy (both addresses 16-byte aligned) onto the mbarrier.  In the common case --
+// every row interior -- and when a warp without stage-2 work exists (`loader`), lane 0 of that
+// warp issues all copies from a short uniform-register loop (about four instructions per copy)
+// while the other warps run stage 2.  Otherwise lane 0 of warp w issues the copies of rows
+// w, w + NWK, ..., and rows that touch a clip edge or the zero padding (at most a handful per
+// clip), and every row of an unaligned input, are filled by their warp through load_sample
+// (reflection / zero fill).
 // Returns bit 0: some rows arrive through the mbarrier, bit 1: some rows were stored by threads.
 template <class G>
 __device__ __forceinline__ int load_tile(float* wave_s, const float* __restrict__ clip, long long s0, int n_samples,
-                                         int valid, bool tma_ok, unsigned long long* bar, int warp, int lane) {
+                                         int valid, bool tma_ok, unsigned long long* bar, int warp, int lane,
+                                         int loader) {
   constexpr int FULL_ROWS = G::SPAN / G::HOP;
   constexpr int REM = G::SPAN - FULL_ROWS * G::HOP;
   constexpr int ROWS = FULL_ROWS + (REM > 0 ? 1 : 0);
@@ -118,16 +133,36 @@ __device__ __forceinline__ int load_tile(float* wave_s, const float* __restrict_
     if (r_lo > r_hi) r_lo = r_hi;
   }
   const int n_tma = r_hi - r_lo;
+  if (n_tma == ROWS && loader >= 0) {
+    if (warp == loader && lane == 0) {
+      fence_proxy_async();    // earlier generic-proxy reads of this buffer are ordered before the async writes
+      mbar_expect_tx(bar, (unsigned)(G::SPAN * 4));
+      unsigned dst = smem_u32(wave_s);
+      const float* src = clip + s0;
+      const unsigned b = smem_u32(bar);
+#pragma unroll 4
+      for (int row = 0; row < FULL_ROWS; ++row, dst += G::PITCH * 4, src += G::HOP)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "n"(G::HOP * 4), "r"(b)
+                     : "memory");
+      if (REM > 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "n"(REM > 0 ? REM * 4 : 16), "r"(b)
+                     : "memory");
+    }
+    __syncwarp();
+    return 1;
+  }
   if (n_tma > 0 && lane == 0) {
-    fence_proxy_async();    // earlier generic-proxy reads of this buffer are ordered before the async writes
+    fence_proxy_async();
     if (warp == 0) {
       const unsigned bytes = (unsigned)(min(r_hi, FULL_ROWS) - r_lo) * (G::HOP * 4u) + (r_hi == ROWS && REM > 0 ? REM * 4u : 0u);
       mbar_expect_tx(bar, bytes);
     }
   }
   if (n_tma == ROWS) {
-    // common case, every row is interior: lane 0 walks this warp's rows with two running pointers
-    if (lane == 0) {
+    // every row is interior: one lane walks this warp's rows with two running pointers
+    if (elect_one()) {
       float* dst = wave_s + warp * G::PITCH;
       const float* src = clip + s0 + warp * G::HOP;
 #pragma unroll 1
@@ -167,11 +202,17 @@ constexpr int kMaxLocalTiles = 64;
 // max(S, clipmax - 8), (S + 4) / 4.
 //
 // Whisper normalisation without a second pass over the data: g(S) = (S + 4) * 0.25 is
-// monotone, so max(g(S), g(M - 8)) == g(max(S, M - 8)) bit for bit.  The first pass therefore
-// stores g(S) -- already final wherever S >= M - 8 -- and records each tile's minimum; once the
-// clip group has agreed on M, only tiles whose minimum lies below M - 8 are revisited with
-// out = max(out, g(M - 8)), while their lines are still in L2.  Silent tiles (all zero padding)
-// are not computed at all: their constant is written once, after M is known.
+// monotone, so max(g(S), g(c)) == g(max(S, c)) bit for bit, and
+//     max(max(S', f), M - 8) == max(S', max(f, M - 8))        (S' = log10 of the UNclamped power,
+//                                                              f = log10(floor))
+// The first pass therefore stores g(S') -- already final wherever S' >= c := max(f, M - 8) --
+// and records each tile's minimum; once the clip group has agreed on M, only tiles whose
+// minimum lies below c are revisited with out = max(out, g(c)), while their lines are still in
+// L2.  The agreement (a release/acquire counter in global memory) is not waited for at the end
+// of the clip: the CTA goes on with the first tile of its next clip and resolves the previous
+// clip afterwards, when the other CTAs of the group have long published their maxima.
+// Silent tiles (all zero padding) are not computed at all: their constant is written when the
+// clip is resolved.
 template <class G, int KIND>
 __global__ void __launch_bounds__(G::THREADS, Lay<G>::MIN_CTAS)
 logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
@@ -187,13 +228,15 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
   __shared__ __align__(8) unsigned long long s_mbar;
   __shared__ float s_red[G::NWK];
   __shared__ float s_max;
-  __shared__ float s_tmin[NORM ? kMaxLocalTiles : 1][G::NWK];
-  __shared__ unsigned char s_silent[NORM ? kMaxLocalTiles : 1];
+  __shared__ float s_cta_max[2];
+  __shared__ float s_tmin[NORM ? 2 : 1][NORM ? kMaxLocalTiles : 1][G::NWK];
+  __shared__ unsigned char s_silent[NORM ? 2 : 1][NORM ? kMaxLocalTiles : 1];
 
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int group_id = blockIdx.x / a.group;
   const int rank = blockIdx.x - group_id * a.group;
+  const int loader = tab.loader_warp;
   const float log_floor = a.log_floor, log_add = a.log_add, log_scale = a.log_scale;
   // what a bin-wise silent frame produces, through exactly the arithmetic of the mel phase
   float silent_val = 0.0f;
@@ -218,14 +261,82 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
   int tl_tile = 0, tl_clip = 0;
 #endif
 
-  for (int clip = group_id; clip < a.batch; clip += a.n_groups) {
+  // this CTA's share of every clip
+  const int t0 = (int)((long long)rank * a.tiles_per_clip / a.group);
+  const int t1 = (int)((long long)(rank + 1) * a.tiles_per_clip / a.group);
+  const bool track = NORM && (t1 - t0 <= kMaxLocalTiles);
+  auto tile_s0 = [&](int t) { return (long long)t * G::F * G::HOP - G::N / 2; };
+
+  // ---- deferred normalisation of a finished clip (NORM only) -------------------------------
+  int pend_clip = -1, pend_valid = 0, pend_par = 0;
+  auto resolve = [&]() {      // CTA-uniform; one CTA barrier inside
+    if (threadIdx.x == 0) {
+      float m;
+      if (a.group > 1) {
+        const float* slots = a.gmax + (long long)pend_clip * a.group;
+        while (ld_acquire(a.gcnt + pend_clip) < a.group) __nanosleep(64);
+        m = __ldcg(slots);
+        for (int r = 1; r < a.group; ++r) m = fmaxf(m, __ldcg(slots + r));
+      } else {
+        m = s_cta_max[pend_par];
+      }
+      m = fmaxf(m, silent_val);                   // the clamp at `floor`, applied to the maximum
+      if (rank == 0 && a.clip_max) a.clip_max[pend_clip] = m;
+      s_max = m;
+    }
+    __syncthreads();
+    // revisit only what the clamp actually touches
+    const float thr = fmaxf(s_max - 8.0f, silent_val);
+    const float cval = vaffine(thr, 0.25f, 1.0f);
+    float* oc = a.out + (long long)pend_clip * a.n_mels * a.n_frames;
+    for (int t = t0; t < t1; ++t) {
+      const int fa = t * G::F;
+      const int len = min(fa + G::F, a.n_frames) - fa;
+      bool silent, fix;
+      if (track) {
+        silent = s_silent[pend_par][t - t0] != 0;
+        float tm = INFINITY;
+        if (!silent)
+          for (int w = 0; w < G::NWK; ++w) tm = fminf(tm, s_tmin[pend_par][t - t0][w]);
+        fix = !(tm >= thr);
+      } else {
+        silent = tile_is_silent<G>(tile_s0(t), a.n_samples, pend_valid);
+        fix = true;
+      }
+      if (silent) {
+        for (int m = warp; m < a.n_mels; m += G::NWK) {
+          float* row = oc + (long long)m * a.n_frames + fa;
+          for (int j = lane; j < len; j += 32) __stcs(row + j, cval);
+        }
+      } else if (fix) {
+        if (a.vec_ok && (len & 3) == 0) {
+          const int q = len >> 2;          // <= 16 float4 per row: two rows per warp pass
+          for (int m = 2 * warp + (lane >> 4); m < a.n_mels; m += 2 * G::NWK) {
+            float4* row = reinterpret_cast<float4*>(oc + (long long)m * a.n_frames + fa);
+            const int j = lane & 15;
+            if (j < q) {
+              float4 v = __ldcg(row + j);
+              v.x = fmaxf(v.x, cval); v.y = fmaxf(v.y, cval); v.z = fmaxf(v.z, cval); v.w = fmaxf(v.w, cval);
+              __stcs(row + j, v);
+            }
+          }
+        } else {
+          for (int m = warp; m < a.n_mels; m += G::NWK) {
+            float* row = oc + (long long)m * a.n_frames + fa;
+            for (int j = lane; j < len; j += 32) row[j] = fmaxf(__ldcg(row + j), cval);
+          }
+        }
+      }
+    }
+    pend_clip = -1;
+  };
+
+  int par = 0;
+  for (int clip = group_id; clip < a.batch; clip += a.n_groups, par ^= 1) {
     const float* cptr = a.wave + (long long)clip * a.clip_stride;
     int valid = a.n_samples;
     if (a.lengths) valid = min(max(a.lengths[clip], 0), a.n_samples);
     float* oc = a.out + (long long)clip * a.n_mels * a.n_frames;
-    const int t0 = (int)((long long)rank * a.tiles_per_clip / a.group);
-    const int t1 = (int)((long long)(rank + 1) * a.tiles_per_clip / a.group);
-    const bool track = NORM && (t1 - t0 <= kMaxLocalTiles);
     float rmax = -INFINITY;
     LM_CSTAMP(0)
     bool staged_tma = false;  // the tile being staged into wave_s arrives through the mbarrier
@@ -233,12 +344,10 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
     // CTA-uniform: start filling wave_s with the tile that begins at sample s; returns whether
     // some rows were written by threads (then a CTA barrier must precede their use)
     auto fetch = [&](long long s) -> bool {
-      const int how = load_tile<G>(wave_s, cptr, s, a.n_samples, valid, a.tma_ok != 0, &s_mbar, warp, lane);
+      const int how = load_tile<G>(wave_s, cptr, s, a.n_samples, valid, a.tma_ok != 0, &s_mbar, warp, lane, loader);
       staged_tma = (how & 1) != 0;
       return (how & 2) != 0;
     };
-
-    auto tile_s0 = [&](int t) { return (long long)t * G::F * G::HOP - G::N / 2; };
     auto next_loud = [&](int t) {            // first tile >= t that has to be computed
       while (t < t1 && tile_is_silent<G>(tile_s0(t), a.n_samples, valid)) ++t;
       return t;
@@ -247,7 +356,7 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
     // ---- silent tiles (all zero padding) are never computed
     for (int t = t0; t < t1; ++t) {
       const bool silent = tile_is_silent<G>(tile_s0(t), a.n_samples, valid);       // CTA-uniform
-      if (NORM && track && threadIdx.x == 0) s_silent[t - t0] = silent ? 1 : 0;
+      if (NORM && track && threadIdx.x == 0) s_silent[par][t - t0] = silent ? 1 : 0;
       if (!silent) continue;
       rmax = fmaxf(rmax, silent_val);
       if (!NORM) {                            // no normalisation: the constant can be written right away
@@ -281,6 +390,13 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
         }
       }
     };
+    // power -> log domain value S (KIND 3: the clamp at `floor` is applied when the clip is resolved)
+    auto to_log = [&](T v) __attribute__((always_inline)) -> T {
+      if (KIND == 1) return vmuls(vlog2_clamp(v, log_floor), log_scale);
+      if (KIND == 2) return vmuls(vlog2_add(v, log_add), log_scale);
+      if (KIND == 3) return vmuls(vlog2_raw(v), log_scale);
+      return v;
+    };
     auto do_mel = [&](int t) __attribute__((always_inline)) {                // mel projection, log, store, running max / tile min
       const int f0 = t * G::F;
       const int f = f0 + lane;
@@ -290,13 +406,11 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
       float tmin = INFINITY;
       if (full) {
         mel_task<G, T>(P, tab, warp, lane, [&](T acc) {
-          T v = acc;
-          if (KIND == 1 || KIND == 3) v = vmuls(vlog2_clamp(v, log_floor), log_scale);
-          if (KIND == 2) v = vmuls(vlog2_add(v, log_add), log_scale);
+          T v = to_log(acc);
           if (NORM) {
             rmax = vhmax(rmax, v);
             tmin = vhmin(tmin, v);
-            v = vmulc(vadds(v, 4.0f), 0.25f);
+            v = vaffine(v, 0.25f, 1.0f);
           }
           op[0] = vlo(v);
           if (G::PK == 2) op[32] = vhi(v);
@@ -305,13 +419,11 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
       } else {
         const bool ok0 = f < a.n_frames, ok1 = (G::PK == 2) && (f + 32 < a.n_frames);
         mel_task<G, T>(P, tab, warp, lane, [&](T acc) {
-          T v = acc;
-          if (KIND == 1 || KIND == 3) v = vmuls(vlog2_clamp(v, log_floor), log_scale);
-          if (KIND == 2) v = vmuls(vlog2_add(v, log_add), log_scale);
+          T v = to_log(acc);
           if (NORM) {
             if (ok0) { rmax = fmaxf(rmax, vlo(v)); tmin = fminf(tmin, vlo(v)); }
             if (ok1) { rmax = fmaxf(rmax, vhi(v)); tmin = fminf(tmin, vhi(v)); }
-            v = vmulc(vadds(v, 4.0f), 0.25f);
+            v = vaffine(v, 0.25f, 1.0f);
           }
           if (ok0) op[0] = vlo(v);
           if (ok1) op[32] = vhi(v);
@@ -321,15 +433,15 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
       if (track) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-        if (lane == 0) s_tmin[t - t0][warp] = tmin;
+        if (lane == 0) s_tmin[par][t - t0][warp] = tmin;
       }
     };
 
     // ---- computed tiles, software pipelined:
     //   S1(t) | barrier | TMA prefetch(t') + S2(t) | barrier | { M(t), S1(t') in either order } | ...
-    // M(t) (shared-memory bound) and S1(t') (FP32-pipe bound) share an interval; one third of the
-    // warps runs them in the opposite order, so the two kinds of work overlap instead of all
-    // warps hitting the same pipe at the same time.
+    // M(t) (shared-memory / MUFU bound) and S1(t') (FP32-pipe bound) share an interval; one third
+    // of the warps runs them in the opposite order, so the two kinds of work overlap instead of
+    // all warps hitting the same pipe at the same time.
     const bool s1_first = ((warp >> 2) & 1) != 0;
     int t = next_loud(t0);
     if (t < t1) {
@@ -338,6 +450,7 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
       LM_STAMP(1)
       do_s1();
     }
+    bool first = true;
     while (t < t1) {
       LM_STAMP(2)
       __syncthreads();                                        // Y(t) complete, waveform tile dead
@@ -353,16 +466,17 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
       LM_STAMP(4)
       __syncthreads();                                        // P(t) complete
       if (!ALIAS) {
-        if (s1_first && pre) {
-          wait_wave();
-          do_s1();
-          do_mel(t);
-        } else {
-          do_mel(t);
-          LM_STAMP(6)
-          if (pre) {
-            wait_wave();
-            do_s1();
+        // one copy of each phase in the instruction stream; the order depends on the warp
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+          if ((ph == 0) == s1_first) {
+            if (pre) {
+              wait_wave();
+              do_s1();
+            }
+          } else {
+            do_mel(t);
+            LM_STAMP(6)
           }
         }
       } else {
@@ -374,6 +488,8 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
           do_s1();
         }
       }
+      if (NORM && first && pend_clip >= 0) resolve();         // the previous clip, one tile into this one
+      first = false;
 #ifdef LM_TIMELINE
       ++tl_tile;
 #endif
@@ -382,7 +498,8 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
 
     LM_CSTAMP(1)
     if (NORM) {
-      // ---- clip maximum: warp shuffle -> CTA -> clip group (release/acquire counter)
+      if (pend_clip >= 0) resolve();                          // this clip had no computed tile
+      // ---- publish this CTA's maximum: warp shuffle -> CTA -> slot of the clip group
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
       if (lane == 0) s_red[warp] = rmax;
@@ -391,67 +508,25 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
         float m = s_red[0];
         for (int w = 1; w < G::NWK; ++w) m = fmaxf(m, s_red[w]);
         if (a.group > 1) {
-          float* slots = a.gmax + (long long)clip * a.group;
-          __stcg(slots + rank, m);
+          __stcg(a.gmax + (long long)clip * a.group + rank, m);
           __threadfence();
           atomicAdd(a.gcnt + clip, 1);
-          while (ld_acquire(a.gcnt + clip) < a.group) __nanosleep(64);
-          for (int r = 0; r < a.group; ++r) m = fmaxf(m, __ldcg(slots + r));
-        }
-        if (rank == 0 && a.clip_max) a.clip_max[clip] = m;
-        s_max = m;
-      }
-      __syncthreads();
-      LM_CSTAMP(2)
-      // ---- revisit only what the clamp actually touches
-      const float thr = s_max - 8.0f;
-      const float cval = (thr + 4.0f) * 0.25f;
-      const float sval = (fmaxf(silent_val, thr) + 4.0f) * 0.25f;
-      for (int t = t0; t < t1; ++t) {
-        const int fa = t * G::F;
-        const int len = min(fa + G::F, a.n_frames) - fa;
-        bool silent, fix;
-        if (track) {
-          silent = s_silent[t - t0] != 0;
-          float tm = INFINITY;
-          if (!silent)
-            for (int w = 0; w < G::NWK; ++w) tm = fminf(tm, s_tmin[t - t0][w]);
-          fix = tm < thr;
         } else {
-          silent = tile_is_silent<G>((long long)fa * G::HOP - G::N / 2, a.n_samples, valid);
-          fix = true;
-        }
-        if (silent) {
-          for (int m = warp; m < a.n_mels; m += G::NWK) {
-            float* row = oc + (long long)m * a.n_frames + fa;
-            for (int j = lane; j < len; j += 32) __stcs(row + j, sval);
-          }
-        } else if (fix) {
-          if (a.vec_ok && (len & 3) == 0) {
-            const int q = len >> 2;          // <= 16 float4 per row: two rows per warp pass
-            for (int m = 2 * warp + (lane >> 4); m < a.n_mels; m += 2 * G::NWK) {
-              float4* row = reinterpret_cast<float4*>(oc + (long long)m * a.n_frames + fa);
-              const int j = lane & 15;
-              if (j < q) {
-                float4 v = __ldcg(row + j);
-                v.x = fmaxf(v.x, cval); v.y = fmaxf(v.y, cval); v.z = fmaxf(v.z, cval); v.w = fmaxf(v.w, cval);
-                __stcs(row + j, v);
-              }
-            }
-          } else {
-            for (int m = warp; m < a.n_mels; m += G::NWK) {
-              float* row = oc + (long long)m * a.n_frames + fa;
-              for (int j = lane; j < len; j += 32) row[j] = fmaxf(__ldcg(row + j), cval);
-            }
-          }
+          s_cta_max[par] = m;
         }
       }
-      __syncthreads();   // s_red / s_max / s_tmin are reused by the next clip
-      LM_CSTAMP(3)
+      pend_clip = clip;
+      pend_valid = valid;
+      pend_par = par;
+      LM_CSTAMP(2)
     }
 #ifdef LM_TIMELINE
     ++tl_clip;
 #endif
+  }
+  if (NORM && pend_clip >= 0) {
+    __syncthreads();          // s_cta_max / s_tmin of the last clip are complete
+    resolve();
   }
 }
 

@@ -92,6 +92,9 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
       t.s2_rows[w][n2[w]++] = (signed char)r.second;
       load[part] += r.first;
     }
+    // A single issuing thread needs ~60 cycles per bulk copy (measured: 66 copies = 4 200 cycles,
+    // longer than stage 2 itself), so the copies stay spread over all warps.
+    t.loader_warp = -1;
   }
   // ---- banded supports
   std::vector<int> lo(n_mels, 0), cnt(n_mels, 0);
@@ -135,7 +138,7 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
   std::vector<long> cost(n_mels);
   long total = 0;
   for (int m = 0; m < n_mels; ++m)
-    total += (cost[m] = scan_ok ? 7L * nbin_of[m] + 19 : 9L * std::max(1, (cnt[m] + 3) / 4) + 14);
+    total += (cost[m] = scan_ok ? 7L * nbin_of[m] + 14 : 9L * std::max(1, (cnt[m] + 3) / 4) + 14);
   {
     int m = 0;
     long acc = 0;
@@ -148,6 +151,13 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
     t.mel_begin[G::NWK] = (unsigned short)n_mels;
   }
   if (scan_ok) {
+    // a(k) may advance by at most two between neighbouring bins (one filter without a bin of
+    // its own); anything wider falls back to the gather form
+    for (int k = 0; k + 1 < G::NBINS; ++k)
+      if (a_of[k + 1] - a_of[k] > 2) scan_ok = false;
+  }
+  if (scan_ok) {
+    Tables<G> keep = t;                      // the gather form below starts from this state
     t.mel_scan = 1;
     for (int k = 0; k < G::NBINS; ++k) {
       const int a = a_of[k];
@@ -155,22 +165,40 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
       t.melw[2 * k + 1] = (a + 1 < n_mels) ? fbank[(size_t)k * n_mels + a + 1] : 0.0f;
     }
     int soff = 0;
-    for (int w = 0; w < G::NWK; ++w) {
+    bool ok = true;
+    for (int w = 0; w < G::NWK && ok; ++w) {
       const int m0 = t.mel_begin[w], m1 = t.mel_begin[w + 1];
+      t.scan_soff[w] = (unsigned short)soff;
+      if (m1 <= m0) continue;
       // bins with a(k) in [m0 - 1, m1 - 1] are contiguous because a(k) never decreases
       int k0 = 0;
       while (k0 < G::NBINS && a_of[k0] < m0 - 1) ++k0;
-      t.scan_bin0[w] = (unsigned short)std::min(k0, G::NBINS - 1);
-      t.scan_soff[w] = (unsigned short)soff;
-      for (int cur = m0 - 1; cur <= m1 - 1; ++cur) {
-        int n = 0;
-        if (m1 > m0 && cur >= 0)
-          for (int k = 0; k < G::NBINS; ++k) n += (a_of[k] == cur);
-        if (n > 255) return "filter bank: a filter segment has more than 255 bins";
-        t.scan_n[soff++] = (unsigned char)n;
+      int k1 = k0;
+      while (k1 < G::NBINS && a_of[k1] <= m1 - 1) ++k1;
+      if (k1 <= k0) { ok = false; break; }
+      t.scan_bin0[w] = (unsigned short)k0;
+      t.scan_nb[w] = (unsigned short)(k1 - k0);
+      if (soff + (k1 - k0) + 4 > kMaxScanSteps) { ok = false; break; }
+      int next_filter = m0;                   // the filter the next emitting shift produces
+      for (int k = k0; k < k1; ++k) {
+        const int cur = a_of[k];
+        const int shifts = (k + 1 < k1) ? a_of[k + 1] - cur : (m1 - 1) - cur + 1;
+        if (shifts < 0 || shifts > 2) { ok = false; break; }
+        unsigned code = 0;
+        for (int j = 0; j < shifts; ++j) {
+          const int f = cur + j;               // filter leaving acc0
+          code |= 1u << j;
+          if (f < m0) code |= 4u << j;         // lead-in: belongs to the previous warp
+          else if (f == next_filter) ++next_filter;
+          else ok = false;
+        }
+        t.scan_code[soff++] = (unsigned char)code;
       }
+      if (next_filter != m1) ok = false;
+      soff = (soff + 3) & ~3;
     }
-    return std::string();
+    if (ok) return std::string();
+    t = keep;                                 // irregular bank: use the gather form
   }
   // ---- gather form: grouped, zero padded weights; a run uses the group count of its widest filter
   int off = 0;

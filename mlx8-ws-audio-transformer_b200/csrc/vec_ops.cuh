@@ -111,6 +111,8 @@ LM_HD float vlog2_clamp(float v, float floor) { return lm_log2(__builtin_fmaxf(v
 LM_HD f32x2 vlog2_clamp(f32x2 v, float floor) {
   return vpack(lm_log2(__builtin_fmaxf(vlo(v), floor)), lm_log2(__builtin_fmaxf(vhi(v), floor)));
 }
+LM_HD float vlog2_raw(float v) { return lm_log2(v); }                      // log2(0) = -inf: clamped later
+LM_HD f32x2 vlog2_raw(f32x2 v) { return vpack(lm_log2(vlo(v)), lm_log2(vhi(v))); }
 LM_HD float vlog2_add(float v, float add) { return lm_log2(v + add); }
 LM_HD f32x2 vlog2_add(f32x2 v, float add) { return vpack(lm_log2(vlo(v) + add), lm_log2(vhi(v) + add)); }
 LM_HD float vhmax(float r, float v) { return __builtin_fmaxf(r, v); }
@@ -126,5 +128,9 @@ LM_HD f32x2 vmuls(f32x2 a, float s) { return vmul(a, vpack(s, s)); }
 LM_HD f32x2 vfmas(f32x2 a, float s, f32x2 c) { return vfma(a, vpack(s, s), c); }
 LM_HD f32x2 vfnmas(f32x2 a, float s, f32x2 c) { return vfma(a, vpack(-s, -s), c); }
 LM_HD f32x2 vadds(f32x2 a, float s) { return vadd(a, vpack(s, s)); }
+// a * k + c with scalar k, c: one FFMA / FFMA2.  With k = 0.25, c = 1 this is bit-identical to
+// (a + 4) / 4 (scaling by a power of two commutes with rounding).
+LM_HD float vaffine(float a, float k, float c) { return __builtin_fmaf(a, k, c); }
+LM_HD f32x2 vaffine(f32x2 a, float k, float c) { return vfma(a, vpack(k, k), vpack(c, c)); }
 
 }  // namespace lm
