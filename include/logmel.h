@@ -72,8 +72,9 @@ typedef struct lm_config {
   int32_t drop_last;         /* 1: emit n_samples/hop frames (Whisper drops frame 3000),
                                 0: emit 1 + n_samples/hop frames (torchaudio)                     */
   int32_t device;            /* CUDA device ordinal                                               */
-  int32_t variant;           /* 0 = default; 1 = one frame per lane (scalar FP32 path),
-                                2 = two frames per lane (packed f32x2 path) -- tuning knob        */
+  int32_t variant;           /* 0 = default (n_fft 400: warp-specialised CTA, two frames per lane);
+                                1 = one frame per lane (scalar FP32 path), 2 = two frames per lane,
+                                phase-synchronous CTA -- tuning / cross-check knob                */
   const float* fbank;        /* host, [n_fft/2+1][n_mels] row-major float32 (mel_filters cast to
                                 f32 / MelScale.fb); copied by lm_create                           */
   const float* window;       /* host, [n_fft] float32, or NULL for the periodic Hann window      */

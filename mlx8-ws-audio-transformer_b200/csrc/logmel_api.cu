@@ -17,6 +17,7 @@
 
 #include "../../include/logmel.h"
 #include "logmel_kernel.cuh"
+#include "logmel_ws_kernel.cuh"
 #include "logmel_tables.h"
 
 namespace {
@@ -45,6 +46,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 constexpr int kMaxGroup = 64;
+constexpr int LM_RETRY_PLAIN = -1000;   // internal: the warp-specialised kernel cannot take this filter bank
 
 struct HostPipe {   // staging for lm_forward_host
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
@@ -71,20 +73,31 @@ struct lm_handle {
 namespace {
 
 template <class G>
+constexpr size_t smem_bytes() {
+  if constexpr (G::WS) return lm::LayWS<G>::BYTES;
+  else return lm::Lay<G>::BYTES;
+}
+
+template <class G>
 struct Impl : lm_handle {
   lm::Tables<G> tab;
   const void* kernel = nullptr;
+  template <int K>
+  static const void* kern() {
+    if constexpr (G::WS) return (const void*)lm::logmel_ws_kernel<G, K>;
+    else return (const void*)lm::logmel_kernel<G, K>;
+  }
   static const void* pick(int log_mode) {
     switch (log_mode) {
-      case LM_LOG_NONE: return (const void*)lm::logmel_kernel<G, 0>;
-      case LM_LN_PLUS_EPS: return (const void*)lm::logmel_kernel<G, 2>;
-      case LM_LOG10_CLAMP: return (const void*)lm::logmel_kernel<G, 1>;
-      default: return (const void*)lm::logmel_kernel<G, 3>;
+      case LM_LOG_NONE: return kern<0>();
+      case LM_LN_PLUS_EPS: return kern<2>();
+      case LM_LOG10_CLAMP: return kern<1>();
+      default: return kern<3>();
     }
   }
   int launch(const lm::KArgs& a, int grid, cudaStream_t st) override {
     void* args[] = {(void*)&tab, (void*)&a};
-    cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(G::THREADS), args, lm::Lay<G>::BYTES, st);
+    cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(G::THREADS), args, smem_bytes<G>(), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchCooperativeKernel(logmel_kernel)");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -99,7 +112,8 @@ int make(lm_handle** out, const lm_config* cfg, const float* window) {
   h->cfg.window = nullptr;
   std::string err = lm::build_tables<G>(h->tab, window, cfg->fbank, cfg->n_mels);
   if (!err.empty()) return fail(LM_ERR_FBANK, "%s", err.c_str());
-  const int smem = (int)lm::Lay<G>::BYTES;
+  if (G::WS && !h->tab.mel_scan) return LM_RETRY_PLAIN;   // in-place stage 2 needs the scan form of the bank
+  const int smem = (int)smem_bytes<G>();
   h->kernel = Impl<G>::pick(cfg->log_mode);
   CUDA_TRY(cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int occ = 0;
@@ -160,6 +174,9 @@ int lm_create(lm_handle** out, const lm_config* cfg) {
   const int v = cfg->variant;
   if (cfg->n_fft == 400 && cfg->hop == 160) {
     if (v == 1) return make<lm::Geo<400, 160, 1>>(out, cfg, win.data());
+    if (v == 2) return make<lm::Geo<400, 160, 2>>(out, cfg, win.data());
+    const int rc = make<lm::Geo<400, 160, 2, 1>>(out, cfg, win.data());   // default: warp-specialised CTA
+    if (rc != LM_RETRY_PLAIN) return rc;
     return make<lm::Geo<400, 160, 2>>(out, cfg, win.data());
   }
   if (cfg->n_fft == 1024 && cfg->hop == 512) return make<lm::Geo<1024, 512, 1>>(out, cfg, win.data());

@@ -35,20 +35,26 @@ template <int NFFT> struct Split;
 template <> struct Split<400> { static constexpr int N1 = 20, N2 = 20; };
 template <> struct Split<1024> { static constexpr int N1 = 32, N2 = 32; };
 
-template <int NFFT, int HOP_, int PK_>
+// WS_ = 1: warp-specialised CTA (logmel_ws_kernel.cuh): warps [0, NW_FFT) run the two DFT stages,
+// warps [NW_FFT, NWK) run the mel projection / log / stores and issue the TMA tile copies.
+template <int NFFT, int HOP_, int PK_, int WS_ = 0>
 struct Geo {
-  static constexpr int N = NFFT, HOP = HOP_, PK = PK_;
+  static constexpr int N = NFFT, HOP = HOP_, PK = PK_, WS = WS_;
   static constexpr int N1 = Split<NFFT>::N1, N2 = Split<NFFT>::N2;
   static constexpr int H1 = N1 / 2;                 // stage-2 tasks are k1 = 0..H1
   static constexpr int NBINS = N / 2 + 1;
   // Warps per CTA: a multiple of 4 so that every SM sub-partition (warp id mod 4) holds the
   // same number of warps; the work tables below balance tasks per sub-partition.
   static constexpr int NWK = (NFFT == 400) ? 12 : 16;
+  static constexpr int NW_FFT = WS_ ? 8 : NWK;      // warps that take stage-1 tasks and stage-2 rows
+  static constexpr int NW_MEL = WS_ ? NWK - 8 : NWK;  // warps that take runs of mel filters
+  static constexpr int MEL_W0 = WS_ ? 8 : 0;        // first of them
   // N = 400: a warp's stage-1 tasks all use the same four columns, so their window samples and
   // twiddles (S1_STRIDE floats per lane) are loaded once per kernel and stay in registers; the
   // alternative -- fetching them from shared memory per task -- costs as many LSU wavefronts as
-  // the waveform samples themselves.  N = 1024 has too many constants (64) for that.
-  static constexpr bool S1_CONST_REGS = (NFFT == 400);
+  // the waveform samples themselves.  N = 1024 has too many constants (64) for that, and the
+  // warp-specialised CTA spreads 20 tasks over 8 warps, which does not split by column group.
+  static constexpr bool S1_CONST_REGS = (NFFT == 400) && !WS_;
   static constexpr int THREADS = NWK * 32;
   static constexpr int F = 32 * PK;                 // frames per tile
   static constexpr int SPAN = (F - 1) * HOP + N;    // samples a tile touches
@@ -72,7 +78,7 @@ struct Geo {
   static constexpr int S1_TASKS = 4 * CGROUPS;
   static constexpr int S1_MAX = 3, S2_MAX = 2;      // most tasks / rows one warp can be handed
   static_assert(N2 % 4 == 0, "columns are handled four at a time");
-  static_assert(S1_TASKS <= NWK * S1_MAX && H1 + 1 <= NWK * S2_MAX, "work tables too small");
+  static_assert(S1_TASKS <= NW_FFT * S1_MAX && H1 + 1 <= NW_FFT * S2_MAX, "work tables too small");
 };
 
 // kernel parameters that live in the constant bank (__grid_constant__)
@@ -105,6 +111,10 @@ struct alignas(16) Tables {
   unsigned short scan_soff[G::NWK];         // multiple of 4
   unsigned short scan_nb[G::NWK];
   alignas(4) unsigned char scan_code[kMaxScanSteps];   // read four codes at a time
+  // Warp-specialised CTA only: where the power of each scanned bin lives.  Stage 2 overwrites
+  // its own row of the real plane of Y with its |X|^2 outputs (row k1, slot j), so bin k is at
+  // row-slot p_slot(k); scan_poff holds that position in BYTES, one entry per scan step.
+  alignas(16) unsigned scan_poff[G::WS ? kMaxScanSteps : 4];
   unsigned char mel_scan;
   signed char s1_tasks[G::NWK][G::S1_MAX];   // stage-1 tasks of each warp (-1: none)
   signed char s2_rows[G::NWK][G::S2_MAX];    // stage-2 rows k1 of each warp (-1: none)
@@ -139,7 +149,7 @@ template <> struct VT<f32x2> {
 };
 
 template <class G> struct ValT { using type = float; };
-template <int N, int H> struct ValT<Geo<N, H, 2>> { using type = f32x2; };
+template <int N, int H, int W> struct ValT<Geo<N, H, 2, W>> { using type = f32x2; };
 
 // ---------------------------------------------------------------------------------------
 // codelet dispatch
@@ -261,6 +271,91 @@ LM_HD void stage1_task(const float* __restrict__ wave_s, T* __restrict__ Y,
   float cst[G::S1_STRIDE];
   stage1_consts<G>(s1tab, task, lane, cst);
   stage1_task_c<G, T>(wave_s, Y, cst, task, lane);
+}
+
+// Same, with the real and imaginary planes of Y given separately (warp-specialised CTA: the
+// real plane is double buffered, see logmel_ws_kernel.cuh).
+template <class G, typename T>
+LM_HD void stage1_compute_ri(const T (&x)[G::N1], T* __restrict__ Yre, T* __restrict__ Yim,
+                             const float (&cst)[G::S1_STRIDE], int task, int lane) {
+  constexpr int N1 = G::N1, N2 = G::N2, H1 = G::H1;
+  const int b = 4 * (task % G::CGROUPS) + (lane >> 3);
+  const int p = 8 * (task / G::CGROUPS) + (lane & 7);
+  float w[N1], tr[H1 + 1], ti[H1 + 1];
+#pragma unroll
+  for (int a = 0; a < N1; ++a) w[a] = cst[a];
+  tr[0] = 1.0f;
+  ti[0] = 0.0f;
+#pragma unroll
+  for (int k = 1; k <= H1; ++k) {
+    tr[k] = cst[N1 + 2 * (k - 1)];
+    ti[k] = cst[N1 + 2 * (k - 1) + 1];
+  }
+  T yr[H1 + 1], yi[H1 + 1];
+  Codelets<G::N>::template s1<T>(x, w, tr, ti, yr, yi);
+  T* dre = Yre + b * 32 + y_slot<G>(p, b);
+  T* dim = Yim + b * 32 + y_slot<G>(p, b);
+#pragma unroll
+  for (int k = 0; k <= H1; ++k) dre[k * N2 * 32] = yr[k];
+#pragma unroll
+  for (int k = 1; k <= H1; ++k) dim[(k - 1) * N2 * 32] = yi[k];
+}
+
+template <class G, typename T>
+LM_HD void stage1_task_ri(const float* __restrict__ wave_s, T* __restrict__ Yre, T* __restrict__ Yim,
+                          const float* __restrict__ s1tab, int task, int lane) {
+  float cst[G::S1_STRIDE];
+  stage1_consts<G>(s1tab, task, lane, cst);
+  T x[G::N1];
+  stage1_load<G, T>(wave_s, task, lane, x);
+  stage1_compute_ri<G, T>(x, Yre, Yim, cst, task, lane);
+}
+
+// row-slot (units of 32 lanes of T, from the start of the real plane) at which the in-place
+// stage 2 leaves the power of bin k: its own row k1, output index j
+template <class G> LM_HD int p_slot(int k) {
+  constexpr int N1 = G::N1, N2 = G::N2, H1 = G::H1, N = G::N;
+  const int c = k % N1, q = k / N1;
+  if (c == 0) return q;                                   // row 0: bins N1 * j
+  if (c < H1) return c * N2 + q;                          // row c, j = q < N2 / 2
+  if (c == H1) return H1 * N2 + q;                        // row H1: bins H1 + N1 * j
+  return (N1 - c) * N2 + ((N - k - (N1 - c)) / N1);       // conjugate side of row N1 - c: j >= N2 / 2
+}
+
+// Stage 2 of row k1 IN PLACE: the row's inputs are read into registers, then its power outputs
+// overwrite the row's own slots of the real plane (output j at slot j).  No other warp touches
+// this row, and a warp's shared-memory accesses are performed in program order.
+template <class G, typename T>
+LM_HD void stage2_task_inplace(T* __restrict__ Yre, const T* __restrict__ Yim, int k1, int lane) {
+  constexpr int N2 = G::N2, H1 = G::H1, N = G::N;
+  T* row = Yre + k1 * N2 * 32;
+  if (k1 == 0) {
+    T yr[N2], p[N2 / 2 + 1];
+#pragma unroll
+    for (int b = 0; b < N2; ++b) yr[b] = row[b * 32 + y_slot<G>(lane, b)];
+    Codelets<N>::template s2_real<T>(yr, p);
+#pragma unroll
+    for (int j = 0; j <= N2 / 2; ++j) row[j * 32 + lane] = p[j];
+    return;
+  }
+  T yr[N2], yi[N2];
+  const T* sim = Yim + (k1 - 1) * N2 * 32;
+#pragma unroll
+  for (int b = 0; b < N2; ++b) {
+    yr[b] = row[b * 32 + y_slot<G>(lane, b)];
+    yi[b] = sim[b * 32 + y_slot<G>(lane, b)];
+  }
+  if (k1 == H1) {
+    T p[N2 / 2];
+    Codelets<N>::template s2_half<T>(yr, yi, p);
+#pragma unroll
+    for (int j = 0; j < N2 / 2; ++j) row[j * 32 + lane] = p[j];
+  } else {
+    T p[N2];
+    Codelets<N>::template s2<T>(yr, yi, p);
+#pragma unroll
+    for (int j = 0; j < N2; ++j) row[j * 32 + lane] = p[j];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -416,6 +511,82 @@ LM_HD void mel_task_scan(const T* __restrict__ P, const Tables<G>& tab, int w, i
     acc1 = vfmas(p0, wp[1], acc1);
     if (c) shift(c);
   }
+}
+
+// Software-pipelined scan for the warp-specialised CTA, where one warp per sub-partition runs the
+// whole mel phase and nothing else hides its latencies:
+//  * bins are fetched in groups of four, one group AHEAD of the arithmetic (power values from
+//    shared memory, weights and codes from the constant bank);
+//  * a finished filter is split into start(acc) -- the part with a long latency (MUFU.LG2) -- and
+//    finish(value), which runs one filter later, when the result has long arrived.
+// Reads up to two groups past the warp's last bin (never used: they follow the last emit); the
+// tables are zero padded and the caller's P is followed by other shared memory.
+template <class G, typename T, class Start, class Finish>
+LM_HD void mel_task_pipe(const T* __restrict__ P, const Tables<G>& tab, int w, int lane, Start&& start,
+                         Finish&& finish) {
+  const int ng = (tab.scan_nb[w] + 3) >> 2;
+  const unsigned* code4 = reinterpret_cast<const unsigned*>(tab.scan_code + tab.scan_soff[w]);
+  const T* src = P + tab.scan_bin0[w] * 32 + lane;
+  const float* wp = tab.melw + 2 * tab.scan_bin0[w];
+  struct Grp {
+    T p[4];
+    float w[8];
+    unsigned c;
+  };
+  // G::WS: P is the in-place output of stage 2 (p_slot layout), addressed through scan_poff
+  const unsigned* poff = tab.scan_poff + (G::WS ? tab.scan_soff[w] : 0);
+  const char* pl = reinterpret_cast<const char*>(P + lane);
+  auto load = [&](Grp& g, int gi) {
+    if (G::WS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g.p[j] = *reinterpret_cast<const T*>(pl + poff[4 * gi + j]);
+    } else {
+      const T* s = src + gi * 128;
+      g.p[0] = s[0]; g.p[1] = s[32]; g.p[2] = s[64]; g.p[3] = s[96];
+    }
+    const float* q = wp + gi * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.w[j] = q[j];
+    g.c = code4[gi];
+  };
+  T acc0 = vzero<T>(), acc1 = vzero<T>(), pend = vzero<T>();
+  bool have = false;
+  auto emit = [&](T acc) {
+    const T cur = start(acc);
+    if (have) finish(pend);
+    pend = cur;
+    have = true;
+  };
+  auto shift = [&](unsigned c) {
+    if (!(c & 4u)) emit(acc0);
+    acc0 = acc1;
+    acc1 = vzero<T>();
+    if (c & 2u) {
+      if (!(c & 8u)) emit(acc0);
+      acc0 = vzero<T>();
+    }
+  };
+  auto run = [&](const Grp& g) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc0 = vfmas(g.p[j], g.w[2 * j], acc0);
+      acc1 = vfmas(g.p[j], g.w[2 * j + 1], acc1);
+      const unsigned c = (g.c >> (8 * j)) & 0xffu;
+      if (c) shift(c);
+    }
+  };
+  Grp ga, gb;
+  if (ng > 0) load(ga, 0);
+  int gi = 0;
+#pragma unroll 1
+  for (; gi + 2 <= ng; gi += 2) {
+    load(gb, gi + 1);
+    run(ga);
+    load(ga, gi + 2);
+    run(gb);
+  }
+  if (gi < ng) run(ga);
+  if (have) finish(pend);
 }
 
 template <class G, typename T, class Emit>

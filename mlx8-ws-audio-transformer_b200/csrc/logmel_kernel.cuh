@@ -115,7 +115,30 @@ __device__ __forceinline__ void bulk_g2s(float* dst_smem, const float* src, unsi
 // clip), and every row of an unaligned input, are filled by their warp through load_sample
 // (reflection / zero fill).
 // Returns bit 0: some rows arrive through the mbarrier, bit 1: some rows were stored by threads.
+// CTA-uniform plan of a tile: rows [r_lo, r_hi) are interior (one bulk copy each), the others are
+// written by threads.  Returns bit 0: some rows arrive through the mbarrier, bit 1: some rows
+// are stored by threads.
 template <class G>
+__device__ __forceinline__ int tile_plan(long long s0, int valid, bool tma_ok, int* r_lo_out, int* r_hi_out) {
+  constexpr int FULL_ROWS = G::SPAN / G::HOP;
+  constexpr int REM = G::SPAN - FULL_ROWS * G::HOP;
+  constexpr int ROWS = FULL_ROWS + (REM > 0 ? 1 : 0);
+  int r_lo = 0, r_hi = 0;
+  if (tma_ok) {
+    r_lo = s0 >= 0 ? 0 : (int)((-s0 + G::HOP - 1) / G::HOP);
+    const long long room = (long long)valid - s0;              // samples of audio from s0 on
+    r_hi = room <= 0 ? 0 : (int)min((long long)FULL_ROWS, room / G::HOP);
+    if (REM > 0 && r_hi == FULL_ROWS && room >= G::SPAN) r_hi = ROWS;
+    if (r_lo > r_hi) r_lo = r_hi;
+  }
+  *r_lo_out = r_lo;
+  *r_hi_out = r_hi;
+  const int n_tma = r_hi - r_lo;
+  return (n_tma > 0 ? 1 : 0) | (n_tma < ROWS ? 2 : 0);
+}
+
+// NW warps (indices 0..NW-1 in `warp`) share the work.
+template <class G, int NW = G::NWK>
 __device__ __forceinline__ int load_tile(float* wave_s, const float* __restrict__ clip, long long s0, int n_samples,
                                          int valid, bool tma_ok, unsigned long long* bar, int warp, int lane,
                                          int loader) {
@@ -166,14 +189,14 @@ __device__ __forceinline__ int load_tile(float* wave_s, const float* __restrict_
       float* dst = wave_s + warp * G::PITCH;
       const float* src = clip + s0 + warp * G::HOP;
 #pragma unroll 1
-      for (int row = warp; row < FULL_ROWS; row += G::NWK, dst += G::NWK * G::PITCH, src += G::NWK * G::HOP)
+      for (int row = warp; row < FULL_ROWS; row += NW, dst += NW * G::PITCH, src += NW * G::HOP)
         bulk_g2s(dst, src, G::HOP * 4, bar);
-      if (REM > 0 && warp == FULL_ROWS % G::NWK)
+      if (REM > 0 && warp == FULL_ROWS % NW)
         bulk_g2s(wave_s + FULL_ROWS * G::PITCH, clip + s0 + FULL_ROWS * G::HOP, REM * 4, bar);
     }
   } else {
 #pragma unroll 1
-    for (int row = warp; row < ROWS; row += G::NWK) {
+    for (int row = warp; row < ROWS; row += NW) {
       const int len = (row < FULL_ROWS) ? G::HOP : REM;
       if (row >= r_lo && row < r_hi) {
         if (lane == 0) bulk_g2s(wave_s + row * G::PITCH, clip + s0 + (long long)row * G::HOP, len * 4, bar);

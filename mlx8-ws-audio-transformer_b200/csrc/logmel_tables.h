@@ -43,7 +43,7 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
     std::vector<long> load(4, 0);
     auto warp_of = [&](int part, const std::vector<int>& cnt, int cap) {   // least-busy warp of a partition
       int best = -1;
-      for (int w = part; w < G::NWK; w += 4)
+      for (int w = part; w < G::NW_FFT; w += 4)
         if (cnt[w] < cap && (best < 0 || cnt[w] < cnt[best])) best = w;
       return best;
     };
@@ -143,12 +143,12 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
     int m = 0;
     long acc = 0;
     t.mel_begin[0] = 0;
-    for (int w = 0; w < G::NWK; ++w) {
-      const long target = total * (w + 1) / G::NWK;
-      while (m < n_mels && (acc + cost[m] / 2 <= target || w == G::NWK - 1)) acc += cost[m++];
+    for (int w = 0; w < G::NW_MEL; ++w) {
+      const long target = total * (w + 1) / G::NW_MEL;
+      while (m < n_mels && (acc + cost[m] / 2 <= target || w == G::NW_MEL - 1)) acc += cost[m++];
       t.mel_begin[w + 1] = (unsigned short)m;
     }
-    t.mel_begin[G::NWK] = (unsigned short)n_mels;
+    for (int w = G::NW_MEL; w <= G::NWK; ++w) t.mel_begin[w] = (unsigned short)n_mels;
   }
   if (scan_ok) {
     // a(k) may advance by at most two between neighbouring bins (one filter without a bin of
@@ -166,7 +166,7 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
     }
     int soff = 0;
     bool ok = true;
-    for (int w = 0; w < G::NWK && ok; ++w) {
+    for (int w = 0; w < G::NW_MEL && ok; ++w) {
       const int m0 = t.mel_begin[w], m1 = t.mel_begin[w + 1];
       t.scan_soff[w] = (unsigned short)soff;
       if (m1 <= m0) continue;
@@ -192,6 +192,7 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
           else if (f == next_filter) ++next_filter;
           else ok = false;
         }
+        if (G::WS) t.scan_poff[soff] = (unsigned)(p_slot<G>(k) * 32 * (int)sizeof(typename ValT<G>::type));
         t.scan_code[soff++] = (unsigned char)code;
       }
       if (next_filter != m1) ok = false;
@@ -202,7 +203,7 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
   }
   // ---- gather form: grouped, zero padded weights; a run uses the group count of its widest filter
   int off = 0;
-  for (int w = 0; w < G::NWK; ++w) {
+  for (int w = 0; w < G::NW_MEL; ++w) {
     const int m0 = t.mel_begin[w], m1 = t.mel_begin[w + 1];
     int ng = 1;
     for (int m = m0; m < m1; ++m) ng = std::max(ng, (cnt[m] + 3) / 4);

@@ -10,7 +10,7 @@ WHISPER, LN = 1, 2
 
 
 @pytest.mark.parametrize("nm", [80, 128])
-@pytest.mark.parametrize("pk", [1, 2])
+@pytest.mark.parametrize("pk", [1, 2, 3])      # 3 = warp-specialised geometry
 def test_emul_whisper_short(emul, golden_whisper_short, nm, pk):
     g = golden_whisper_short
     names = [str(n) for n in g["names"]]

@@ -43,7 +43,7 @@ def fronts():
 # golden vectors (outputs of the live HF / torchaudio calls, committed under tests/golden)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nm", [80, 128])
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_whisper_short_golden(golden_whisper_short, fronts, nm, variant):
     g = golden_whisper_short
     names = [str(n) for n in g["names"]]
@@ -77,7 +77,7 @@ def test_whisper_dropin_call_golden(golden_whisper_short, nm):
 
 
 @pytest.mark.parametrize("nm", [80, 128])
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_whisper_30s_golden(golden_whisper_30s, fronts, nm, variant):
     g = golden_whisper_30s
     x = np.concatenate([synth.gaussian_clips(3, seed=0), synth.midi_piano_clips(2, seed=0)[0],
@@ -157,9 +157,10 @@ def test_lengths_truncation_and_short_clips(fronts):
         _assert_parity(fe.forward(torch.from_numpy(w).cuda()), O.whisper_logmel(w, n_mels=80, n_samples=L), f"L={L}")
 
 
-def test_batch_position_group_size_and_paths_are_bit_identical(fronts):
+@pytest.mark.parametrize("variant", [0, 2])
+def test_batch_position_group_size_and_paths_are_bit_identical(fronts, variant):
     """A clip's features do not depend on batch size, batch position, CTA grouping or entry point."""
-    fe = fronts(128, 2)
+    fe = fronts(128, variant)
     x = torch.from_numpy(synth.gaussian_clips(40, seed=41)).cuda()
     full = fe.forward(x)
     torch.cuda.synchronize()
