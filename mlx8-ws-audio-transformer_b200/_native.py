@@ -15,7 +15,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "liblogmel_b200.so")
+LIB_PATH = os.environ.get("LM_LIB_PATH") or os.path.join(CSRC, "liblogmel_b200.so")   # override: tuning builds only
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "logmel.h")
 
 NVCC_FLAGS = [

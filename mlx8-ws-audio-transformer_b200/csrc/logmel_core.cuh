@@ -119,6 +119,10 @@ struct alignas(16) Tables {
   signed char s1_tasks[G::NWK][G::S1_MAX];   // stage-1 tasks of each warp (-1: none)
   signed char s2_rows[G::NWK][G::S2_MAX];    // stage-2 rows k1 of each warp (-1: none)
   signed char loader_warp;                   // a warp without stage-2 rows issues the tile's TMA copies (-1: none)
+  // warp-specialised CTA: the FFT warps with ONE stage-2 row issue the TMA copies of the next tile
+  // (tma_iss: their number 0..n_tma_iss-1, -1 for the others) while the two-row warps start stage 2
+  signed char tma_iss[G::NWK];
+  signed char n_tma_iss;
 };
 
 // ---------------------------------------------------------------------------------------

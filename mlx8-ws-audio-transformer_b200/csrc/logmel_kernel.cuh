@@ -33,11 +33,14 @@ struct KArgs {
 };
 
 #ifdef LM_TIMELINE
+#ifndef LM_TL_CTA
+#define LM_TL_CTA 0
+#endif
 #define LM_STAMP(slot)                                                                         \
-  if (a.timeline && blockIdx.x == 0 && lane == 0 && tl_tile < 48)                              \
+  if (a.timeline && blockIdx.x == LM_TL_CTA && lane == 0 && tl_tile < 48)                              \
     a.timeline[(tl_tile * 16 + warp) * 8 + (slot)] = clock64();
 #define LM_CSTAMP(slot)                                                                        \
-  if (a.timeline && blockIdx.x == 0 && threadIdx.x == 0 && tl_clip < 16)                       \
+  if (a.timeline && blockIdx.x == LM_TL_CTA && threadIdx.x == 0 && tl_clip < 16)                       \
     a.timeline[48 * 16 * 8 + tl_clip * 8 + (slot)] = clock64();
 #else
 #define LM_STAMP(slot)
@@ -138,10 +141,12 @@ __device__ __forceinline__ int tile_plan(long long s0, int valid, bool tma_ok, i
 }
 
 // NW warps (indices 0..NW-1 in `warp`) share the work.
+// n_iss > 0: in the common all-interior case only n_iss of them issue copies (this warp is number
+// `iss` among those, -1 if it is not one) -- the warps with the lighter stage-2 load.
 template <class G, int NW = G::NWK>
 __device__ __forceinline__ int load_tile(float* wave_s, const float* __restrict__ clip, long long s0, int n_samples,
                                          int valid, bool tma_ok, unsigned long long* bar, int warp, int lane,
-                                         int loader) {
+                                         int loader, int iss = -1, int n_iss = 0) {
   constexpr int FULL_ROWS = G::SPAN / G::HOP;
   constexpr int REM = G::SPAN - FULL_ROWS * G::HOP;
   constexpr int ROWS = FULL_ROWS + (REM > 0 ? 1 : 0);
@@ -185,13 +190,14 @@ __device__ __forceinline__ int load_tile(float* wave_s, const float* __restrict_
   }
   if (n_tma == ROWS) {
     // every row is interior: one lane walks this warp's rows with two running pointers
-    if (elect_one()) {
-      float* dst = wave_s + warp * G::PITCH;
-      const float* src = clip + s0 + warp * G::HOP;
+    const int me = n_iss > 0 ? iss : warp, step = n_iss > 0 ? n_iss : NW;
+    if (me >= 0 && elect_one()) {
+      float* dst = wave_s + me * G::PITCH;
+      const float* src = clip + s0 + me * G::HOP;
 #pragma unroll 1
-      for (int row = warp; row < FULL_ROWS; row += NW, dst += NW * G::PITCH, src += NW * G::HOP)
+      for (int row = me; row < FULL_ROWS; row += step, dst += step * G::PITCH, src += step * G::HOP)
         bulk_g2s(dst, src, G::HOP * 4, bar);
-      if (REM > 0 && warp == FULL_ROWS % NW)
+      if (REM > 0 && me == FULL_ROWS % step)
         bulk_g2s(wave_s + FULL_ROWS * G::PITCH, clip + s0 + FULL_ROWS * G::HOP, REM * 4, bar);
     }
   } else {

@@ -95,6 +95,18 @@ std::string build_tables(Tables<G>& t, const float* window, const float* fbank, 
     // A single issuing thread needs ~60 cycles per bulk copy (measured: 66 copies = 4 200 cycles,
     // longer than stage 2 itself), so the copies stay spread over all warps.
     t.loader_warp = -1;
+    {
+      int n = 0;
+      for (int w = 0; w < G::NWK; ++w) t.tma_iss[w] = -1;
+      if (G::WS)
+        for (int w = 0; w < G::NW_FFT; ++w)
+          if (n2[w] <= 1) t.tma_iss[w] = (signed char)n++;
+      if (n < 3) {                      // too few light warps: everybody issues
+        n = 0;
+        for (int w = 0; w < G::NWK; ++w) t.tma_iss[w] = -1;
+      }
+      t.n_tma_iss = (signed char)n;
+    }
   }
   // ---- banded supports
   std::vector<int> lo(n_mels, 0), cnt(n_mels, 0);
