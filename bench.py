@@ -205,6 +205,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     fe = LogMelFrontend(400, 160, slaney_mel_filter_bank(201, N_MELS), N.LOG10_CLAMP_WHISPER_NORM, 1e-10, True,
@@ -283,7 +285,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "kernel": info, "variant": args.variant, "checksum": checksum},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if not traffic else traffic.get("dram_bytes_per_launch"),
-                         "peak_source": peak_src, "kernel": "lm::logmel_kernel<Geo<400,160,*>>",
+                         "peak_source": peak_src, "kernel": "lm::logmel_ws_kernel<Geo<400,160,2,1>,3>",
                          "algorithmic_bytes_per_launch": BYTES_PER_CLIP * B, "kernel_ms": kern_ms,
                          "kernel_ms_min": min(step_ms), "traffic_source": None if not traffic else traffic.get("source")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eb * N_SAMPLES * 4,
