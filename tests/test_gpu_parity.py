@@ -207,6 +207,34 @@ def test_full_size_properties():
     assert torch.equal(fe.forward(x[300:]), y[300:])               # contiguous shard == slice of the whole
 
 
+@pytest.mark.parametrize("nm", [80, 128])
+def test_clamp_everywhere_one_cta_per_clip(nm):
+    """> 148 clips (every CTA owns whole clips) whose quiet parts lie > 80 dB under one loud burst:
+    every tile is revisited by the max-8 pass after the clip maximum is known."""
+    fe = LogMelFrontend(400, 160, O.slaney_mel_filter_bank(201, nm), N.LOG10_CLAMP_WHISPER_NORM, 1e-10, True)
+    B = 300
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, 480000, generator=g, device="cuda") * 1e-5
+    t = torch.arange(400, device="cuda") / 16000.0
+    pos = torch.randint(0, 479000, (B,), generator=torch.Generator().manual_seed(6))
+    pos[7] = pos[9] = 1000                                           # keep these two bursts inside what survives below
+    for i in range(B):
+        x[i, pos[i]:pos[i] + 400] += 0.9 * torch.sin(2 * np.pi * (300.0 + 20 * i) * t)
+    x[7, 200000:] = 0.0                                              # silent tiles inside such a clip
+    lengths = torch.full((B,), 480000, dtype=torch.int32, device="cuda")
+    lengths[9] = 123457
+    y = fe.forward(x, lengths=lengths)
+    torch.cuda.synchronize()
+    flat = y.reshape(B, -1)
+    assert torch.isfinite(y).all()
+    assert ((flat.max(dim=1).values - flat.min(dim=1).values) - 2.0).abs().max() < 1e-5   # clamp active in every clip
+    sub = [0, 7, 9, 151, 299]
+    xs = x[sub].cpu().numpy()
+    xs[2, 123457:] = 0.0
+    _assert_parity(y[sub], O.whisper_logmel(xs, n_mels=nm), "clamped subset")
+    assert torch.equal(fe.forward(x[150:], lengths=lengths[150:]), y[150:])
+
+
 def test_cls_transformer_consumer_logits():
     """Config 3: features feed the CLS-token encoder of spectrogram.py:944-1057 ([B, n_mels, T] input)."""
     w, lengths = synth.urbansound_clips(8, seed=3)
