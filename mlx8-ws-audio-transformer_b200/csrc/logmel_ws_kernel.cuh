@@ -146,12 +146,11 @@ logmel_ws_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
         }
       };
 
+      // (one call site of do_s1 -- one copy of the stage-1 codelet in the instruction stream)
       int t = next_loud(t0);
-      if (t < t1) {
-        fetch(tile_s0(t));
-        do_s1(it);
-      }
+      if (t < t1) fetch(tile_s0(t));
       while (t < t1) {
+        do_s1(it);
         LM_STAMP(2)
         nbar_sync(BAR_YDONE, NTF);                 // Y(it) complete, waveform tile dead
         const int tn = next_loud(t + 1);
@@ -169,7 +168,6 @@ logmel_ws_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
         nbar_arrive((it & 1) ? BAR_PFULL1 : BAR_PFULL0, NT);      // P(it) is in Yre[it & 1]
         nbar_sync(BAR_S2DONE, NTF);                // every FFT warp is done reading Yim
         ++it;
-        if (pre) do_s1(it);
 #ifdef LM_TIMELINE
         ++tl_tile;
 #endif
