@@ -33,10 +33,11 @@
 // Cycles by which the FFT warps with the lighter stage-1 load (two tasks instead of three) start
 // stage 1 late.  All FFT warps leave the same barrier and run the same load -> math -> store
 // sequence, so without an offset the two warps of a sub-partition ask for the LSU at the same time
-// and for the FP32 pipe at the same time; 250-400 cycles measured best (0: -1.8 % throughput,
-// 650+: the delayed warps become the critical path).
+// and for the FP32 pipe at the same time.  Measured with one CTA per clip, ms per 4096 clips:
+// 0: 5.66, 100: 5.56, 200: 5.45, 250: 5.48, 350: 5.51, 500: 5.52 (650+: the delayed warps become
+// the critical path).
 #ifndef LM_STAGGER1
-#define LM_STAGGER1 350
+#define LM_STAGGER1 200
 #endif
 
 namespace lm {
