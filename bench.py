@@ -44,6 +44,14 @@ UNIT = "clips/s"
 WORKLOAD = "whisper-large-v3 128-mel log-mel, 4096 synthetic 30 s 16 kHz clips per GPU (BASELINE configs[1])"
 
 
+def set_mels(n: int):
+    """side measurements on the 80-mel shape; the default run is untouched"""
+    global N_MELS, BYTES_PER_CLIP, WORKLOAD
+    N_MELS = n
+    BYTES_PER_CLIP = N_SAMPLES * 4 + N_MELS * N_FRAMES * 4
+    WORKLOAD = f"whisper {n}-mel log-mel, synthetic 30 s 16 kHz clips (side measurement, not BASELINE configs[1])"
+
+
 def load_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -312,7 +320,11 @@ def main():
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU per step")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (lm_config.variant)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mels", type=int, default=N_MELS, choices=[80, 128],
+                    help="128 = BASELINE configs[1] (the headline); 80 = the Whisper-tiny shape of configs[0]/[4], side measurement")
     args = ap.parse_args()
+    if args.mels != N_MELS:
+        set_mels(args.mels)
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
