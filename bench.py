@@ -213,8 +213,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs to stdout by default: keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     fe = LogMelFrontend(400, 160, slaney_mel_filter_bank(201, N_MELS), N.LOG10_CLAMP_WHISPER_NORM, 1e-10, True,
