@@ -52,6 +52,28 @@ def set_mels(n: int):
     WORKLOAD = f"whisper {n}-mel log-mel, synthetic 30 s 16 kHz clips (side measurement, not BASELINE configs[1])"
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner) write to fd 1; send all of that to stderr and keep the real
+    stdout for the one JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def load_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -196,7 +218,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -213,7 +235,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs to stdout by default: keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     fe = LogMelFrontend(400, 160, slaney_mel_filter_bank(201, N_MELS), N.LOG10_CLAMP_WHISPER_NORM, 1e-10, True,
@@ -304,7 +326,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -328,14 +350,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-    if world != args.gpus and world == 1 and args.gpus > 1:
+    if args.impl == "ours" and world != args.gpus and world == 1 and args.gpus > 1:
         # convenience: re-launch under torchrun when asked for N > 1 from a plain python call
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    quiet_stdout()
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
     run_ours(args, rank, local_rank, world)
 
 
