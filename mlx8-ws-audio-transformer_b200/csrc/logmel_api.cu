@@ -19,6 +19,7 @@
 #include "../../include/logmel.h"
 #include "logmel_kernel.cuh"
 #include "logmel_ws_kernel.cuh"
+#include "logmel_tf_kernel.cuh"
 #include "logmel_tables.h"
 
 namespace {
@@ -62,14 +63,37 @@ struct HostPipe {   // staging for lm_forward_host
 
 }  // namespace
 
+// The thread-per-frame kernel (logmel_tf_kernel.cuh): attached to a Whisper handle when the filter
+// bank has one of the two generated sparsity patterns; lm_forward picks it for batches that give
+// every warp of the grid at least one clip.
+struct TfLauncher {
+  lm::TfTables tab;
+  const void* kernel = nullptr;        // frames per clip read from the arguments
+  const void* kernel3000 = nullptr;    // 30 s clips: the store offsets are immediates
+  int n_mels = 0, n_sm = 0;
+  int launch(const lm::KArgs& a, cudaStream_t st);
+};
+
 struct lm_handle {
   lm_config cfg{};
   int n_sm = 0, ctas_per_sm = 0, smem = 0, threads = 0, frames_per_tile = 0;
   std::mutex host_mu;
   HostPipe pipe;
+  std::unique_ptr<TfLauncher> tf;
+  long long tf_min_batch = 0;        // smallest batch routed to the thread-per-frame kernel
   virtual ~lm_handle() {}
   virtual int launch(const lm::KArgs& a, int grid, cudaStream_t st) = 0;
 };
+
+int TfLauncher::launch(const lm::KArgs& a, cudaStream_t st) {
+  void* args[] = {(void*)&tab, (void*)&a};
+  const int grid = (int)std::min<long long>(n_sm, (a.batch + lm::TfGeo::PAIRS - 1) / lm::TfGeo::PAIRS);
+  cudaError_t e = cudaLaunchKernel(a.n_frames == 3000 ? kernel3000 : kernel, dim3(grid), dim3(lm::TfGeo::THREADS), args,
+                                   lm::TfGeo::SMEM_REQUEST, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel(logmel_tf_kernel)");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
 
 namespace {
 
@@ -132,6 +156,64 @@ int make(lm_handle** out, const lm_config* cfg, const float* window) {
   return 0;
 }
 
+template <int NM>
+bool tf_fill(lm::TfTables& t, const float* window, const float* fbank) {
+  using P = lm::TfMelPattern<NM>;
+  int nnz = 0;
+  for (int k = 0; k < 201; ++k)
+    for (int m = 0; m < NM; ++m) nnz += fbank[(size_t)k * NM + m] != 0.0f;
+  if (nnz != P::NNZ) return false;
+  for (int i = 0; i < P::NNZ; ++i) {       // the kernel's mel weights are literals: the bank must be THAT bank
+    unsigned bits;
+    std::memcpy(&bits, &fbank[(size_t)P::bin[i] * NM + P::mel[i]], 4);
+    if (bits != P::bits[i]) return false;
+  }
+  for (int cp = 0; cp < 10; ++cp) {
+    for (int a = 0; a < 20; ++a) {
+      const float w0 = window[20 * a + 2 * cp], w1 = window[20 * a + 2 * cp + 1];
+      t.w[cp][a] = lm::tf_pack2(w0, w1);
+      t.nw[cp][a] = lm::tf_pack2(-w0, -w1);
+    }
+    for (int k = 1; k <= 10; ++k) {
+      float c[2], s[2];
+      for (int h = 0; h < 2; ++h) {      // same rounding as build_tables(): cos / sin in double, rounded once
+        const double ang = -2.0 * M_PI * (double)(2 * cp + h) * (double)k / 400.0;
+        c[h] = (float)std::cos(ang);
+        s[h] = (float)std::sin(ang);
+      }
+      t.twr[cp][k - 1] = lm::tf_pack2(c[0], c[1]);
+      t.ntwr[cp][k - 1] = lm::tf_pack2(-c[0], -c[1]);
+      t.twi[cp][k - 1] = lm::tf_pack2(s[0], s[1]);
+      t.ntwi[cp][k - 1] = lm::tf_pack2(-s[0], -s[1]);
+    }
+  }
+  return true;
+}
+
+// returns 0 with h->tf set when the bank qualifies, 0 with h->tf empty when it does not
+int attach_tf(lm_handle* h, const lm_config* cfg, const float* window) {
+  if (cfg->log_mode != LM_LOG10_CLAMP_WHISPER_NORM || (cfg->n_mels != 80 && cfg->n_mels != 128)) return 0;
+  auto t = std::make_unique<TfLauncher>();
+  std::memset(&t->tab, 0, sizeof(t->tab));
+  const bool ok = cfg->n_mels == 80 ? tf_fill<80>(t->tab, window, cfg->fbank) : tf_fill<128>(t->tab, window, cfg->fbank);
+  if (!ok) return 0;
+  t->kernel = cfg->n_mels == 80 ? (const void*)lm::logmel_tf_kernel<80, 0> : (const void*)lm::logmel_tf_kernel<128, 0>;
+  t->kernel3000 = cfg->n_mels == 80 ? (const void*)lm::logmel_tf_kernel<80, 3000> : (const void*)lm::logmel_tf_kernel<128, 3000>;
+  t->n_mels = cfg->n_mels;
+  t->n_sm = h->n_sm;
+  CUDA_TRY(cudaFuncSetAttribute(t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm::TfGeo::SMEM_REQUEST));
+  CUDA_TRY(cudaFuncSetAttribute(t->kernel3000, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm::TfGeo::SMEM_REQUEST));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t->kernel, lm::TfGeo::THREADS, lm::TfGeo::SMEM_REQUEST));
+  if (occ != 1) return fail(LM_ERR_NO_DEVICE, "thread-per-frame kernel: %d CTAs per SM (expected exactly 1: the CTA owns all of TMEM)", occ);
+  h->tf = std::move(t);
+  // every warp pair of the grid (4 per SM) should own at least one clip; below that the CTA-tiled
+  // kernel, which spreads a clip over many CTAs, is faster
+  h->tf_min_batch = (long long)h->n_sm * lm::TfGeo::PAIRS;
+  if (const char* e = std::getenv("LM_TF_MIN_BATCH")) h->tf_min_batch = std::max(1, atoi(e));   // tuning knob
+  return 0;
+}
+
 int64_t frames_for(const lm_config& c, int64_t n_samples) {
   return 1 + n_samples / c.hop - (c.drop_last ? 1 : 0);
 }
@@ -182,9 +264,19 @@ int lm_create(lm_handle** out, const lm_config* cfg) {
   if (cfg->n_fft == 400 && cfg->hop == 160) {
     if (v == 1) return make<lm::Geo<400, 160, 1>>(out, cfg, win.data());
     if (v == 2) return make<lm::Geo<400, 160, 2>>(out, cfg, win.data());
-    const int rc = make<lm::Geo<400, 160, 2, 1>>(out, cfg, win.data());   // default: warp-specialised CTA
-    if (rc != LM_RETRY_PLAIN) return rc;
-    return make<lm::Geo<400, 160, 2>>(out, cfg, win.data());
+    int rc = make<lm::Geo<400, 160, 2, 1>>(out, cfg, win.data());   // CTA-tiled default: warp-specialised CTA
+    if (rc == LM_RETRY_PLAIN) rc = make<lm::Geo<400, 160, 2>>(out, cfg, win.data());
+    if (rc != 0) return rc;
+    rc = attach_tf(*out, cfg, win.data());                            // + thread-per-frame kernel for large batches
+    if (rc == 0 && v == 3) {
+      if (!(*out)->tf) rc = fail(LM_ERR_FBANK, "variant 3 (thread-per-frame kernel) needs the Whisper normalisation and the 80- or 128-filter Slaney bank");
+      else (*out)->tf_min_batch = 1;
+    }
+    if (rc != 0) {
+      lm_destroy(*out);
+      *out = nullptr;
+    }
+    return rc;
   }
   if (cfg->n_fft == 1024 && cfg->hop == 512) return make<lm::Geo<1024, 512, 1>>(out, cfg, win.data());
   if (cfg->n_fft == 1024 && cfg->hop == 128) return make<lm::Geo<1024, 128, 1>>(out, cfg, win.data());
@@ -292,9 +384,16 @@ int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_st
   if (norm) {
     a.gcnt = reinterpret_cast<int*>(d_scratch);
     a.gmax = reinterpret_cast<float*>(d_scratch) + ((batch + 3) / 4) * 4;
-    CUDA_TRY(cudaMemsetAsync(a.gcnt, 0, (size_t)batch * sizeof(int), st));
   }
-  int rc = h->launch(a, a.group * a.n_groups, st);
+  int rc;
+  const int64_t tf_tiles = (n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F;
+  if (h->tf && a.tma_ok && batch >= h->tf_min_batch && tf_tiles <= lm::kTfMaxTiles) {
+    a.tiles_per_clip = (int)tf_tiles;
+    rc = h->tf->launch(a, st);
+  } else {
+    if (norm) CUDA_TRY(cudaMemsetAsync(a.gcnt, 0, (size_t)batch * sizeof(int), st));
+    rc = h->launch(a, a.group * a.n_groups, st);
+  }
   if (dev != c.device && dev >= 0) cudaSetDevice(dev);
   return rc;
 }

@@ -1,0 +1,515 @@
+// Thread-per-frame form of the fused Whisper log-mel kernel: the steady-state hot path.
+//
+// The CTA-tiled kernels (logmel_kernel.cuh, logmel_ws_kernel.cuh) spread one frame over many
+// threads, so the two transposes of the two-stage FFT (samples -> columns, columns -> rows) and
+// the bin order of the mel projection all go through shared memory with index tables: ncu r01 shows
+// them bound by shared-memory wavefronts (52 %) and FP32 issue (48 %) TOGETHER, and 60 % of their
+// instructions are not floating point.  Here ONE THREAD OWNS ONE FRAME from the waveform to the
+// stored features, and a warp owns 32 consecutive frames of one clip:
+//
+//   stage 1   the thread reads its 400 samples with LDS.128 (row pitch 164 floats: 41 quad-words,
+//             odd, so the 8 lanes of a quarter-warp phase hit 8 different 16-byte banks) and runs
+//             the windowed real DFT-20 of two adjacent columns at a time, packed in f32x2
+//             (FFMA2/FADD2; the LDS.128 result registers ARE the packed pairs).  Window samples
+//             and twiddles are the same for every lane => uniform-register operands (LDCU), no
+//             shared-memory constants.
+//   transpose the 420 inter-stage values of the frame are parked in TENSOR MEMORY, used as
+//             lane-private scratch: warp w of the CTA owns TMEM lanes 32w..32w+31, lane = frame,
+//             column = (row k1, re/im, column b).  tcgen05.st / tcgen05.ld with the 32x32b shape
+//             are exactly "each thread writes / reads N consecutive words of its own lane", so the
+//             column -> row transpose costs no shared-memory bandwidth, no swizzle and no barrier
+//             (tools/microbench/tmem_scratch.cu: no MMA is needed to use TMEM; 220-350 B/cycle/SM).
+//   stage 2   per row k1: 40 values back from TMEM, complex DFT-20 + |X|^2 in scalar FP32 (same
+//             FMA-pipe time as the packed form), power written over the row in place.
+//   mel       straight-line banded projection generated for the two Whisper banks
+//             (tf_mel_gen.cuh): weights are constant-bank operands, the n_mels sums of the frame
+//             live in registers; then log2 * scale, running clip max / tile min, (S+4)/4 and a
+//             store that is coalesced across the warp (lane = consecutive frame).
+//
+// Two warps share a tile of 32 frames (and a TMEM lane quadrant, which one frame's 420 values nearly
+// fill): both have lane = frame, role A takes column pairs 0-4 / rows 0-4,10 / the low filters, role B
+// column pairs 5-9 / rows 5-9 / the high filters, and they meet at three 64-thread named barriers
+// per tile.  The two warps sit on the same SM sub-partition, so whenever one waits for shared or
+// tensor memory the other issues.  A pair walks a whole clip, so the Whisper max - 8 rule needs no
+// inter-CTA agreement (the per-tile minimum decides which tiles are revisited, as in the other
+// kernels).  The waveform tile of the next 32 frames is fetched with cp.async (16-byte chunks,
+// coalesced) while stage 2 / mel of the current one run.  Grid: one CTA of 4 pairs per SM (the CTA
+// owns all 512 TMEM columns).
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#include "logmel_kernel.cuh"
+#include "tf_mel_gen.cuh"
+
+namespace lm {
+
+struct TfGeo {
+  static constexpr int N = 400, HOP = 160, N1 = 20, N2 = 20, H1 = 10;
+  static constexpr int F = 32;                          // frames per warp tile: lane = frame
+  static constexpr int SPAN = (F - 1) * HOP + N;        // 5360 samples
+  static constexpr int PITCH = HOP + 4;                 // 164 floats = 41 quad-words (odd)
+  static constexpr int ROWS = (SPAN + HOP - 1) / HOP;   // 34
+  static constexpr int TILE_FLOATS = ROWS * PITCH;
+  static constexpr int PAIRS = 4;                       // warp pairs per CTA = TMEM lane quadrants
+  static constexpr int WARPS = 2 * PAIRS;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int Y_COLS = N2 + 2 * N2 * H1;       // 420 TMEM columns per frame
+  static constexpr size_t SMEM = (size_t)PAIRS * TILE_FLOATS * 4;
+  // ask for more than half of the SM's shared memory so that two CTAs (each allocating all of
+  // TMEM) can never be co-resident
+  static constexpr size_t SMEM_REQUEST = SMEM > 120 * 1024 ? SMEM : 120 * 1024;
+};
+constexpr int kTfMaxTiles = 128;
+
+// stage-1 constants of column pair c = b / 2, packed (b, b + 1); twiddles of k1 = 1..10 at [k1 - 1]
+// (each entry is the 64-bit image of an f32x2: low word = column b, high word = column b + 1, so a
+// constant reaches the FFMA2 as one aligned uniform-register pair without any packing move)
+struct alignas(16) TfTables {
+  unsigned long long w[10][20], nw[10][20];
+  unsigned long long twr[10][10], ntwr[10][10], twi[10][10], ntwi[10][10];
+};
+__host__ __device__ inline unsigned long long tf_pack2(float lo, float hi) {
+  unsigned a, b;
+  memcpy(&a, &lo, 4);
+  memcpy(&b, &hi, 4);
+  return (unsigned long long)a | ((unsigned long long)b << 32);
+}
+
+// ---- tensor memory as lane-private scratch -------------------------------------------------
+#define LM_TM_R4(r, o) "f"(r[o]), "f"(r[o + 1]), "f"(r[o + 2]), "f"(r[o + 3])
+#define LM_TM_W4(r, o) "=f"(r[o]), "=f"(r[o + 1]), "=f"(r[o + 2]), "=f"(r[o + 3])
+__device__ __forceinline__ void tm_st2(uint32_t addr, float a, float b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void tm_st4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t addr, const float* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr),
+               LM_TM_R4(r, 0), LM_TM_R4(r, 4)
+               : "memory");
+}
+__device__ __forceinline__ void tm_st16(uint32_t addr, const float* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};" ::"r"(addr),
+      LM_TM_R4(r, 0), LM_TM_R4(r, 4), LM_TM_R4(r, 8), LM_TM_R4(r, 12)
+      : "memory");
+}
+__device__ __forceinline__ void tm_ld4(uint32_t addr, float* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : LM_TM_W4(r, 0) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tm_ld8(uint32_t addr, float* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : LM_TM_W4(r, 0), LM_TM_W4(r, 4)
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void tm_ld16(uint32_t addr, float* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : LM_TM_W4(r, 0), LM_TM_W4(r, 4), LM_TM_W4(r, 8), LM_TM_W4(r, 12)
+      : "r"(addr)
+      : "memory");
+}
+__device__ __forceinline__ void tm_ld32(uint32_t addr, float* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : LM_TM_W4(r, 0), LM_TM_W4(r, 4), LM_TM_W4(r, 8), LM_TM_W4(r, 12), LM_TM_W4(r, 16), LM_TM_W4(r, 20),
+        LM_TM_W4(r, 24), LM_TM_W4(r, 28)
+      : "r"(addr)
+      : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// TMEM columns of a frame.  Row 0 of Y is real: 20 columns, column b at [b].  Rows k1 = 1..10 take 40
+// columns each; a stage-1 codelet produces the two adjacent columns (b, b + 1) = column pair cp
+// as packed pairs (re b, re b+1) and (im b, im b+1), which go out with ONE 4-column store:
+//   [base(k1) + 4 cp + {0, 1, 2, 3}] = re(2cp), re(2cp+1), im(2cp), im(2cp+1)
+// Stage 2 reads the 40 columns of a row with two loads; the order is a compile-time renaming.
+__device__ __forceinline__ constexpr int tf_row_base(int k1) { return k1 == 0 ? 0 : 20 + 40 * (k1 - 1); }
+__device__ __forceinline__ constexpr int tf_re(int b) { return 4 * (b / 2) + (b & 1); }
+__device__ __forceinline__ constexpr int tf_im(int b) { return 4 * (b / 2) + 2 + (b & 1); }
+
+// one stage-1 codelet: columns (2 CP, 2 CP + 1) of this lane's frame; every table offset and
+// every tensor-memory column is a compile-time constant (uniform-register operands, no index math)
+template <int CP, class TabRef>
+__device__ __forceinline__ void tf_stage1_pair(const TabRef& tab, const float4 (&x4)[20], uint32_t tm) {
+  f32x2 x[20], w[20], nw[20], twr[11], ntwr[11], twi[11], ntwi[11], yr[11], yi[11];
+#pragma unroll
+  for (int i = 0; i < 20; ++i) {
+    x[i] = (CP & 1) == 0 ? vpack(x4[i].x, x4[i].y) : vpack(x4[i].z, x4[i].w);
+    w[i] = vfrombits(tab.w[CP][i]);
+    nw[i] = vfrombits(tab.nw[CP][i]);
+  }
+  twr[0] = ntwr[0] = twi[0] = ntwi[0] = vzero<f32x2>();     // unused by the codelet
+#pragma unroll
+  for (int k = 1; k <= 10; ++k) {
+    twr[k] = vfrombits(tab.twr[CP][k - 1]);
+    ntwr[k] = vfrombits(tab.ntwr[CP][k - 1]);
+    twi[k] = vfrombits(tab.twi[CP][k - 1]);
+    ntwi[k] = vfrombits(tab.ntwi[CP][k - 1]);
+  }
+  stage1_r20p<f32x2>(x, w, twr, twi, ntwi, nw, ntwr, yr, yi);
+  tm_st2(tm + 2 * CP, vlo(yr[0]), vhi(yr[0]));
+#pragma unroll
+  for (int k = 1; k <= 10; ++k) tm_st4(tm + tf_row_base(k) + 4 * CP, vlo(yr[k]), vhi(yr[k]), vlo(yi[k]), vhi(yi[k]));
+}
+
+__device__ __forceinline__ void tf_load_group(const float* mine, int g4, float4 (&x4)[20]) {
+#pragma unroll
+  for (int i = 0; i < 20; ++i) {
+    const int n = 20 * i;       // sample n = 20 i + 4 g4 .. + 3 of the frame; a hop row holds 160 samples + 4 pad
+    x4[i] = *reinterpret_cast<const float4*>(mine + n + 4 * (n / TfGeo::HOP) + 4 * g4);
+  }
+}
+
+// one row k1 = 1..9 of stage 2: 40 columns in, complex DFT-20, |X|^2, 20 columns out (in place)
+__device__ __forceinline__ void tf_stage2_row(uint32_t base) {
+  float y[40], yr[20], yi[20], p[20];
+  tm_ld32(base, y);
+  tm_ld8(base + 32, y + 32);
+  tm_wait_ld();
+#pragma unroll
+  for (int b = 0; b < 20; ++b) {
+    yr[b] = y[tf_re(b)];
+    yi[b] = y[tf_im(b)];
+  }
+  stage2_c20<float>(yr, yi, p);
+  tm_st16(base, p);
+  tm_st4(base + 16, p[16], p[17], p[18], p[19]);
+}
+
+__device__ __forceinline__ void pair_sync(int pair) {     // the two warps of a pair: named barrier 1 + pair
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+}
+
+// mel projection of role R over the 11 rows of P, then log / clip statistics / store
+template <int NM, int R>
+__device__ __forceinline__ void tf_mel_store(uint32_t tm, float* op, long long ostep, float q_scale, float& hi_out,
+                                             float& lo_out) {
+  using P = TfMelPattern<NM>;
+  constexpr int M0 = R == 0 ? 0 : P::M0, M1 = R == 0 ? P::M0 : NM;
+  float acc[P::MAXHALF];
+#pragma unroll
+  for (int m = 0; m < P::MAXHALF; ++m) acc[m] = 0.0f;
+  float pa[20], pb[20];
+#pragma unroll
+  for (int j = 0; j < 20; ++j) pa[j] = pb[j] = 0.0f;
+  tm_ld8(tm, pa);
+  tm_ld4(tm + 8, pa + 8);
+  tm_wait_ld();
+  // rows alternate between two register sets: the next row is on its way while this one is used
+#define LM_TF_ROW(K1, CUR, NXT)                                          \
+  if (K1 < 9) {                                                          \
+    tm_ld16(tm + tf_row_base(K1 + 1), NXT);                              \
+    tm_ld4(tm + tf_row_base(K1 + 1) + 16, NXT + 16);                     \
+  } else if (K1 == 9) {                                                  \
+    tm_ld8(tm + tf_row_base(10), NXT);                                   \
+    tm_ld4(tm + tf_row_base(10) + 8, NXT + 8);                           \
+  }                                                                      \
+  tf_mel_row<NM, K1, R>(CUR, acc);                                       \
+  if (K1 < 10) tm_wait_ld();
+  LM_TF_ROW(0, pa, pb)
+  LM_TF_ROW(1, pb, pa)
+  LM_TF_ROW(2, pa, pb)
+  LM_TF_ROW(3, pb, pa)
+  LM_TF_ROW(4, pa, pb)
+  LM_TF_ROW(5, pb, pa)
+  LM_TF_ROW(6, pa, pb)
+  LM_TF_ROW(7, pb, pa)
+  LM_TF_ROW(8, pa, pb)
+  LM_TF_ROW(9, pb, pa)
+  LM_TF_ROW(10, pa, pb)
+#undef LM_TF_ROW
+  // running maximum / tile minimum of log2(mel): four independent chains of 3-input min / max
+  float hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+  op += M0 * ostep;
+#pragma unroll
+  for (int m = 0; m < M1 - M0; m += 2) {
+    const float l0 = vlog2_raw(acc[m]), l1 = vlog2_raw(acc[m + 1]);
+    hi[(m >> 1) & 3] = fmaxf(fmaxf(hi[(m >> 1) & 3], l0), l1);
+    lo[(m >> 1) & 3] = fminf(fminf(lo[(m >> 1) & 3], l0), l1);
+    op[m * ostep] = vaffine(l0, q_scale, 1.0f);
+    op[(m + 1) * ostep] = vaffine(l1, q_scale, 1.0f);
+  }
+  hi_out = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
+  lo_out = fminf(fminf(lo[0], lo[1]), fminf(lo[2], lo[3]));
+}
+
+// NM: 80 or 128 (the two generated banks).  NF: frames per clip when known at compile time (3000:
+// the store offsets m * NF become immediates), 0: read from the arguments.
+// Whisper normalisation: log10, clip max - 8, (S + 4) / 4.
+template <int NM, int NF>
+__global__ void __launch_bounds__(TfGeo::THREADS, 1)
+logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
+  using G = TfGeo;
+  using MP = TfMelPattern<NM>;
+#ifdef LM_TF_SMEM_CONST
+  // stage-1 constants as shared-memory operands (warp-uniform LDS) instead of uniform-register loads
+  __shared__ TfTables s_tab;
+  for (int i = threadIdx.x; i < (int)(sizeof(TfTables) / 8); i += blockDim.x)
+    reinterpret_cast<unsigned long long*>(&s_tab)[i] = reinterpret_cast<const unsigned long long*>(&ctab)[i];
+  const TfTables& tab = s_tab;
+#else
+  const TfTables& tab = ctab;
+#endif
+  static_assert(MP::M0 % 2 == 0 && NM % 2 == 0, "the epilogue walks filters two at a time");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_tmin[G::PAIRS][kTfMaxTiles][2];
+  __shared__ float s_pmax[G::PAIRS][2];
+
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int pair = warp & 3;                 // = TMEM lane quadrant = SM sub-partition of both warps
+  const int role = warp >> 2;                // 0: A, 1: B
+  float* tile = reinterpret_cast<float*>(smem_raw) + pair * G::TILE_FLOATS;
+
+  // ---- the CTA takes the whole tensor memory of its SM: 512 columns x 128 lanes
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = __shfl_sync(0xffffffffu, s_tmem + ((uint32_t)(pair * 32) << 16), 0);   // the pair's lane quadrant
+
+  const float log_floor = a.log_floor, log_scale = a.log_scale;
+  const float silent_val = vlog2_clamp(0.0f, log_floor) * log_scale;
+  const float q_scale = 0.25f * log_scale;          // (S + 4) / 4 with S = log2 * scale, one FFMA
+  const int n_frames = NF ? NF : a.n_frames;
+  const int T = a.tiles_per_clip;
+  auto tile_s0 = [&](int t) { return (long long)t * G::F * G::HOP - G::N / 2; };
+
+  // cp.async plan of four hop rows (160 16-byte chunks, five per lane): byte offsets in the tile
+  unsigned dst_off[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int i = lane + 32 * j;
+    dst_off[j] = smem_u32(tile) + (unsigned)((i / 40) * G::PITCH * 4 + (i % 40) * 16);
+  }
+
+  const int gp = pair * gridDim.x + blockIdx.x;                     // pairs of an SM take clips 148 apart
+  const int gn = gridDim.x * G::PAIRS;
+  for (int clip = gp; clip < a.batch; clip += gn) {
+    const float* cptr = a.wave + (long long)clip * a.clip_stride;
+    int valid = a.n_samples;
+    if (a.lengths) valid = min(max(a.lengths[clip], 0), a.n_samples);
+    float* oc = a.out + (long long)clip * NM * n_frames;
+    float rmax = -INFINITY;                   // of log2(mel), this warp's filters
+    auto next_loud = [&](int t) {
+      while (t < T && tile_is_silent<G>(tile_s0(t), a.n_samples, valid)) ++t;
+      return t;
+    };
+    // Filling the pair's waveform tile (dead at that point) with tile t, half of it per warp.  Hop rows
+    // inside the audio arrive as coalesced 16-byte cp.async chunks: four rows = 160 chunks = five per
+    // lane per call of fetch_rows4 -- a burst of all twenty stalls the warp on the LSU queue (ncu:
+    // lg_throttle 8 % of the kernel), so the steady state issues one group of five behind each
+    // stage-2 row.  Tiles that touch a clip edge (reflection) or the zero padding are written by
+    // the lanes, row by row, at once.
+    const char* fsrc = nullptr;        // interior tile being fetched: this warp's first chunk; else nullptr
+    auto fetch_rows4 = [&](int blk) {  // rows 4 blk .. 4 blk + 3 of this warp's half (blk 4, role B: rows 32, 33)
+      if (!fsrc) return;
+      const unsigned rb = (role * 4 + blk) * (4 * G::PITCH * 4);
+      const char* src = fsrc + blk * (4 * G::HOP * 4);
+      if (blk < 4) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_off[j] + rb), "l"(src + 512 * j) : "memory");
+      } else if (role == 1) {          // the last one is half a row: 60 chunks
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_off[0] + rb), "l"(src) : "memory");
+        if (lane < 28) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_off[1] + rb), "l"(src + 512) : "memory");
+      }
+    };
+    auto fetch_begin = [&](int t) {
+      const long long s0 = tile_s0(t);
+      fsrc = nullptr;
+      if (s0 >= 0 && s0 + G::SPAN <= valid) {
+        fsrc = reinterpret_cast<const char*>(cptr + s0) + 16 * lane + role * (4 * 4 * G::HOP * 4);
+        return;
+      }
+#pragma unroll 1
+      for (int r = role; r < G::ROWS; r += 2) {
+        const long long sr = s0 + (long long)r * G::HOP;
+        const int len = r == G::ROWS - 1 ? G::SPAN - (G::ROWS - 1) * G::HOP : G::HOP;
+        float* drow = tile + r * G::PITCH;
+        if (sr >= 0 && sr + len <= valid) {
+          for (int c = lane; c < len / 4; c += 32) cp_async16(drow + 4 * c, cptr + sr + 4 * c);
+        } else {
+          for (int i = lane; i < len; i += 32) drow[i] = load_sample(cptr, (long)(sr + i), a.n_samples, valid);
+        }
+      }
+    };
+
+    int t = next_loud(0);
+    if (t < T) {
+      fetch_begin(t);
+#pragma unroll 1
+      for (int blk = 0; blk < 5; ++blk) fetch_rows4(blk);
+      cp_async_commit();
+    }
+    while (t < T) {
+      cp_async_wait_all();
+      pair_sync(pair);           // the tile is complete; the partner has finished reading P of the previous tile
+      // Lanes past the clip's last frame (only in its last tile) redo the last valid frame: same
+      // samples, same arithmetic, the same value stored to the same address -- no predicates anywhere.
+      const int fl = min(lane, n_frames - 1 - t * G::F);
+      // ================= stage 1: wave tile -> Y in tensor memory =================
+      {
+        const float* mine = tile + fl * G::PITCH;
+        // (a rolled loop over a switch: one basic block per unit keeps ptxas from hoisting the constant
+        //  loads of later column pairs over earlier ones and running out of uniform registers)
+#pragma unroll 1
+        for (int u = 0; u < 3; ++u) {
+          float4 x4[20];
+          switch (role * 3 + u) {
+            case 0: tf_load_group(mine, 0, x4); tf_stage1_pair<0>(tab, x4, tm); tf_stage1_pair<1>(tab, x4, tm); break;
+            case 1: tf_load_group(mine, 1, x4); tf_stage1_pair<2>(tab, x4, tm); tf_stage1_pair<3>(tab, x4, tm); break;
+            case 2: tf_load_group(mine, 2, x4); tf_stage1_pair<4>(tab, x4, tm); break;
+            case 3: tf_load_group(mine, 2, x4); tf_stage1_pair<5>(tab, x4, tm); break;
+            case 4: tf_load_group(mine, 3, x4); tf_stage1_pair<6>(tab, x4, tm); tf_stage1_pair<7>(tab, x4, tm); break;
+            default: tf_load_group(mine, 4, x4); tf_stage1_pair<8>(tab, x4, tm); tf_stage1_pair<9>(tab, x4, tm); break;
+          }
+        }
+      }
+      tm_wait_st();
+      pair_sync(pair);           // Y is complete, the waveform tile is dead
+      const int tn = next_loud(t + 1);
+      fsrc = nullptr;
+      if (tn < T) fetch_begin(tn);   // the copies themselves go out between the stage-2 rows
+
+      // ================= stage 2: rows of Y -> |X|^2, in place =================
+      if (role == 0) {
+        {
+          float yr[20], p[12], pr[11];
+          tm_ld16(tm, yr);
+          tm_ld4(tm + 16, yr + 16);
+          tm_wait_ld();
+          stage2_r20_half<float>(yr, pr);
+#pragma unroll
+          for (int j = 0; j < 11; ++j) p[j] = pr[j];
+          p[11] = 0.0f;
+          tm_st8(tm, p);
+          tm_st4(tm + 8, p[8], p[9], p[10], p[11]);
+        }
+#pragma unroll 1
+        for (int k1 = 1; k1 <= 4; ++k1) {
+          fetch_rows4(k1 - 1);
+          tf_stage2_row(tm + (uint32_t)(20 + 40 * (k1 - 1)));
+        }
+        {
+          const uint32_t base = tm + (uint32_t)tf_row_base(10);
+          float y[40], yr[20], yi[20], p[12], ph[10];
+          tm_ld32(base, y);
+          tm_ld8(base + 32, y + 32);
+          tm_wait_ld();
+#pragma unroll
+          for (int b = 0; b < 20; ++b) {
+            yr[b] = y[tf_re(b)];
+            yi[b] = y[tf_im(b)];
+          }
+          stage2_c20_half<float>(yr, yi, ph);
+#pragma unroll
+          for (int j = 0; j < 10; ++j) p[j] = ph[j];
+          p[10] = p[11] = 0.0f;
+          tm_st8(base, p);
+          tm_st4(base + 8, p[8], p[9], p[10], p[11]);
+        }
+      } else {
+#pragma unroll 1
+        for (int k1 = 5; k1 <= 9; ++k1) {
+          fetch_rows4(k1 - 5);
+          tf_stage2_row(tm + (uint32_t)(20 + 40 * (k1 - 1)));
+        }
+      }
+      cp_async_commit();
+      tm_wait_st();
+      pair_sync(pair);           // P is complete
+
+      // ================= mel projection, log, store =================
+      {
+        float* op = oc + (t * G::F + fl);
+        float hi, lo;
+        if (role == 0) tf_mel_store<NM, 0>(tm, op, (long long)n_frames, q_scale, hi, lo);
+        else tf_mel_store<NM, 1>(tm, op, (long long)n_frames, q_scale, hi, lo);
+        rmax = fmaxf(rmax, hi);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        if (lane == 0) s_tmin[pair][t][role] = lo * log_scale;
+      }
+      t = tn;
+    }
+
+    // ================= the clip is complete: max - 8 clamp where it bites =================
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    if (lane == 0) s_pmax[pair][role] = rmax * log_scale;
+    pair_sync(pair);
+    const float cmax = fmaxf(fmaxf(s_pmax[pair][0], s_pmax[pair][1]), silent_val);   // the clamp at `floor`, applied to the maximum
+    if (role == 0 && lane == 0 && a.clip_max) a.clip_max[clip] = cmax;
+    const float thr = fmaxf(cmax - 8.0f, silent_val);
+    const float cval = vaffine(thr, 0.25f, 1.0f);
+    const int mA = role == 0 ? 0 : MP::M0, mB = role == 0 ? MP::M0 : NM;            // this warp's filters
+    for (int tt = 0; tt < T; ++tt) {
+      const int fa = tt * G::F;
+      const int len = min(fa + G::F, n_frames) - fa;
+      if (tile_is_silent<G>(tile_s0(tt), a.n_samples, valid)) {
+        for (int m = mA; m < mB; ++m) {
+          float* row = oc + (long long)m * n_frames + fa;
+          if (lane < len) __stcs(row + lane, cval);
+        }
+        continue;
+      }
+      // the stored values are fma(log2, scale / 4, 1), the minimum was taken on log2 * scale: leave
+      // a margin of a few ulps so that rounding can never skip a tile that needs the clamp
+      if (s_tmin[pair][tt][role] > thr + 1e-5f) continue;   // (a NaN minimum takes the fix-up path)
+      if (a.vec_ok && (len & 3) == 0) {
+        const int q = len >> 2, j = lane & 7;         // <= 8 float4 per row: four rows per warp pass
+        constexpr int UNR = 8;
+        for (int m0 = mA + (lane >> 3); m0 < mB; m0 += 4 * UNR) {
+          float4 v[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int m = m0 + 4 * u;
+            if (m < mB && j < q) v[u] = __ldcg(reinterpret_cast<const float4*>(oc + (long long)m * n_frames + fa) + j);
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int m = m0 + 4 * u;
+            if (m < mB && j < q) {
+              float4 w = v[u];
+              w.x = fmaxf(w.x, cval); w.y = fmaxf(w.y, cval); w.z = fmaxf(w.z, cval); w.w = fmaxf(w.w, cval);
+              __stcs(reinterpret_cast<float4*>(oc + (long long)m * n_frames + fa) + j, w);
+            }
+          }
+        }
+      } else {
+        for (int m = mA; m < mB; ++m) {
+          float* row = oc + (long long)m * n_frames + fa;
+          if (lane < len) row[lane] = fmaxf(__ldcg(row + lane), cval);
+        }
+      }
+    }
+    pair_sync(pair);             // s_pmax / s_tmin may be rewritten by the next clip
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(512) : "memory");
+}
+
+}  // namespace lm

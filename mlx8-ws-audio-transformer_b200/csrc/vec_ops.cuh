@@ -96,6 +96,18 @@ LM_HD f32x2 vfma(f32x2 a, f32x2 b, f32x2 c) {
 #endif
 
 template <> LM_HD f32x2 vzero<f32x2>() { return vpack(0.0f, 0.0f); }
+// the 64-bit image of a pair (low word = first element), as stored in constant tables
+LM_HD f32x2 vfrombits(unsigned long long b) {
+  f32x2 r;
+#if defined(__CUDA_ARCH__)
+  r.v = b;
+#else
+  const unsigned lo = (unsigned)b, hi = (unsigned)(b >> 32);
+  __builtin_memcpy(&r.lo, &lo, 4);
+  __builtin_memcpy(&r.hi, &hi, 4);
+#endif
+  return r;
+}
 
 // ---- epilogue helpers: log2 of a clamped / offset value, horizontal max / min ------------
 LM_HD float lm_log2(float x) {   // x is a normal positive number here

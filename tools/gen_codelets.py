@@ -262,6 +262,7 @@ class Codelet:
         self.params = []          # (kind, cname, count)  kind in {"in", "sin", "out"}
         self.scalars = set()      # ids of scalar-typed input nodes
         self.outputs = []         # (cexpr, V)
+        self.neg_twin = {}        # input array -> array holding its negation (packed constants)
 
     def inputs(self, cname, count, scalar=False):
         """declare an input array; ``scalar`` inputs are plain floats shared by both packed
@@ -367,7 +368,17 @@ class Codelet:
                     p, q = q, p
                 fn = {"mulv": "vmul", "fmav": "vfma", "fnmav": "vfnma"}[n.op] + ("s" if sc else "")
                 rest = "" if n.op == "mulv" else f", {a[2].name}"
-                e = f"{fn}({p.name}, {q.name}{rest})"
+                pn, qn = p.name, q.name
+                if n.op == "fnmav" and not sc:
+                    # c - p*q with q (or p) a packed constant that has a negated twin: one FFMA2
+                    for cand in (q, p):
+                        arr = cand.name.split("[")[0] if cand.op == "in" else None
+                        if arr in self.neg_twin:
+                            neg = cand.name.replace(arr + "[", self.neg_twin[arr] + "[", 1)
+                            other = p if cand is q else q
+                            pn, qn, fn = other.name, neg, "vfma"
+                            break
+                e = f"{fn}({pn}, {qn}{rest})"
             elif n.op == "fmac":
                 e = f"vfmac({a[0].name}, {_lit(a[1])}, {a[2].name})"
             lines.append(f"  const T {n.name} = {e};")
@@ -386,8 +397,12 @@ def _lit(k: float) -> str:
     return f"{k:.9e}f"
 
 
-def make_stage1(n1: int, n2_total: int):
+def make_stage1(n1: int, n2_total: int, packed_consts: bool = False):
     """windowed real DFT over the coarse index + inter-stage twiddle.
+
+    packed_consts: the thread-per-frame kernel packs two COLUMNS (b, b+1) in one f32x2, so the
+    window samples and twiddles differ between the two halves and are of type T themselves; the
+    negated twiddle sine comes in as its own input (FFMA2 has no operand negation).
 
     in : x[n1]  samples x[N2*a + b] of one frame (b = this warp's column)
          w[n1]  window values w[N2*a + b]
@@ -395,19 +410,31 @@ def make_stage1(n1: int, n2_total: int):
     out: yr/yi[n1/2+1]    Y[b][k1] * W_N^{b*k1}, k1 = 0..n1/2
     """
     half = n1 // 2
-    c = Codelet(f"stage1_r{n1}",
-                f"stage 1 of N={n1 * n2_total}: window, real DFT-{n1}, twiddle; outputs k1=0..{half}")
+    c = Codelet(f"stage1_r{n1}" + ("p" if packed_consts else ""),
+                f"stage 1 of N={n1 * n2_total}: window, real DFT-{n1}, twiddle; outputs k1=0..{half}"
+                + ("; packed (per-half) constants" if packed_consts else ""))
     x = c.inputs("x", n1)
-    w = c.inputs("w", n1, scalar=True)
-    twr = c.inputs("twr", half + 1, scalar=True)
-    twi = c.inputs("twi", half + 1, scalar=True)
+    w = c.inputs("w", n1, scalar=not packed_consts)
+    twr = c.inputs("twr", half + 1, scalar=not packed_consts)
+    twi = c.inputs("twi", half + 1, scalar=not packed_consts)
+    ntwi = c.inputs("ntwi", half + 1, scalar=False) if packed_consts else None
+    if packed_consts:
+        c.inputs("nw", n1, scalar=False)          # -w: turns c - x*w into one FFMA2 (see Codelet.emit)
+        c.inputs("ntwr", half + 1, scalar=False)
+        c.neg_twin = {"w": "nw", "twi": "ntwi", "ntwi": "twi", "twr": "ntwr"}
     c.out_array("yr", half + 1)
     c.out_array("yi", half + 1)
     zero = V(c.g, None)
     xs = [C(x[a].mulv(w[a]), zero) for a in range(n1)]
     y = dft(xs)
     for k1 in range(half + 1):
-        v = y[k1] if k1 == 0 else y[k1].mulv(twr[k1], twi[k1])
+        if k1 == 0:
+            v = y[k1]
+        elif packed_consts:
+            z = y[k1]
+            v = C(z.re.mulv(twr[k1]) + z.im.mulv(ntwi[k1]), z.re.mulv(twi[k1]) + z.im.mulv(twr[k1]))
+        else:
+            v = y[k1].mulv(twr[k1], twi[k1])
         c.emit_out(f"yr[{k1}]", v.re)
         c.emit_out(f"yi[{k1}]", v.im)
     return c
@@ -440,6 +467,8 @@ def build_all():
     cl = []
     for n1, n2 in ((20, 20), (32, 32)):
         cl.append(make_stage1(n1, n2))
+        if n1 == 20:
+            cl.append(make_stage1(n1, n2, packed_consts=True))
         cl.append(make_stage2(n2, f"stage2_c{n2}", False, list(range(n2))))
         cl.append(make_stage2(n2, f"stage2_c{n2}_half", False, list(range(n2 // 2))))
         cl.append(make_stage2(n2, f"stage2_r{n2}_half", True, list(range(n2 // 2 + 1))))
@@ -478,7 +507,12 @@ def selftest():
             for k1 in range(half + 1):
                 ref = sum(arrays["x"][a] * arrays["w"][a] * cmath.exp(-2j * math.pi * a * k1 / n1)
                           for a in range(n1))
-                if k1:
+                if k1 and "ntwi" in arrays:
+                    tw = complex(arrays["twr"][k1], arrays["twi"][k1])
+                    # the codelet is told -twi separately; a consistent table has ntwi == -twi
+                    ref = complex(ref.real * tw.real + ref.imag * arrays["ntwi"][k1],
+                                  ref.real * tw.imag + ref.imag * tw.real)
+                elif k1:
                     ref *= complex(arrays["twr"][k1], arrays["twi"][k1])
                 err = max(err, abs(ref - complex(res[f"yr[{k1}]"], res[f"yi[{k1}]"])))
         else:
