@@ -72,9 +72,14 @@ typedef struct lm_config {
   int32_t drop_last;         /* 1: emit n_samples/hop frames (Whisper drops frame 3000),
                                 0: emit 1 + n_samples/hop frames (torchaudio)                     */
   int32_t device;            /* CUDA device ordinal                                               */
-  int32_t variant;           /* 0 = default (n_fft 400: warp-specialised CTA, two frames per lane);
-                                1 = one frame per lane (scalar FP32 path), 2 = two frames per lane,
-                                phase-synchronous CTA -- tuning / cross-check knob                */
+  int32_t variant;           /* 0 = default: for the Whisper normalisation with the 80- / 128-filter
+                                Slaney bank, batches of >= 4 clips per SM run the thread-per-frame
+                                kernel (tensor memory as transpose scratch), everything else the
+                                CTA-tiled kernels (n_fft 400: warp-specialised CTA, two frames per lane);
+                                1 = CTA-tiled, one frame per lane (scalar FP32 path), 2 = CTA-tiled,
+                                two frames per lane, phase-synchronous CTA, 3 = thread-per-frame
+                                kernel for every batch size -- tuning / cross-check knobs.
+                                The kernels agree to float32 rounding (<= 1e-6), not bit for bit.  */
   const float* fbank;        /* host, [n_fft/2+1][n_mels] row-major float32 (mel_filters cast to
                                 f32 / MelScale.fb); copied by lm_create                           */
   const float* window;       /* host, [n_fft] float32, or NULL for the periodic Hann window      */
@@ -122,6 +127,9 @@ int lm_host_unregister(void* p);
 int64_t lm_launch_count(void);
 int lm_kernel_info(const lm_handle* h, int32_t* n_sm, int32_t* ctas_per_sm, int32_t* smem_bytes,
                    int32_t* threads, int32_t* frames_per_tile);
+/* name (as ncu / cuobjdump print it) of the kernel lm_forward launches for `batch` 16-byte aligned
+ * clips of n_samples; the string belongs to the handle */
+const char* lm_kernel_name(const lm_handle* h, int64_t batch, int64_t n_samples);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 SYMBOLS = [
     "lm_version", "lm_last_error", "lm_create", "lm_destroy", "lm_num_frames", "lm_scratch_bytes",
     "lm_forward", "lm_forward_host", "lm_host_register", "lm_host_unregister", "lm_launch_count",
-    "lm_kernel_info",
+    "lm_kernel_info", "lm_kernel_name",
 ]
 
 LOG_NONE, LOG10_CLAMP_WHISPER_NORM, LN_PLUS_EPS, LOG10_CLAMP = 0, 1, 2, 3
@@ -112,6 +112,8 @@ def lib() -> ctypes.CDLL:
         L.lm_launch_count.restype = i64
         L.lm_kernel_info.argtypes = [vp, i32p, i32p, i32p, i32p, i32p]
         L.lm_kernel_info.restype = ctypes.c_int
+        L.lm_kernel_name.argtypes = [vp, i64, i64]
+        L.lm_kernel_name.restype = ctypes.c_char_p
         _lib = L
     return _lib
 

@@ -81,6 +81,7 @@ struct lm_handle {
   HostPipe pipe;
   std::unique_ptr<TfLauncher> tf;
   long long tf_min_batch = 0;        // smallest batch routed to the thread-per-frame kernel
+  std::string tiled_name;            // the CTA-tiled kernel of this handle, as profilers print it
   virtual ~lm_handle() {}
   virtual int launch(const lm::KArgs& a, int grid, cudaStream_t st) = 0;
 };
@@ -147,6 +148,12 @@ int make(lm_handle** out, const lm_config* cfg, const float* window) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
   if (!prop.cooperativeLaunch) return fail(LM_ERR_NO_DEVICE, "device lacks cooperative launch");
+  {
+    char nm[96];
+    snprintf(nm, sizeof(nm), "lm::%s<lm::Geo<%d, %d, %d, %d>, %d>", G::WS ? "logmel_ws_kernel" : "logmel_kernel", G::N, G::HOP,
+             G::PK, G::WS, cfg->log_mode == LM_LOG_NONE ? 0 : cfg->log_mode == LM_LN_PLUS_EPS ? 2 : cfg->log_mode == LM_LOG10_CLAMP ? 1 : 3);
+    h->tiled_name = nm;
+  }
   h->n_sm = prop.multiProcessorCount;
   h->ctas_per_sm = occ;
   h->smem = smem;
@@ -216,6 +223,12 @@ int attach_tf(lm_handle* h, const lm_config* cfg, const float* window) {
 
 int64_t frames_for(const lm_config& c, int64_t n_samples) {
   return 1 + n_samples / c.hop - (c.drop_last ? 1 : 0);
+}
+
+// the thread-per-frame kernel takes the launch when the handle has one, the clips are 16-byte
+// aligned (cp.async), the batch gives every warp pair a clip and a clip has at most kTfMaxTiles tiles
+bool use_tf(const lm_handle* h, int64_t batch, int64_t n_frames, bool aligned) {
+  return h->tf && aligned && batch >= h->tf_min_batch && (n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F <= lm::kTfMaxTiles;
 }
 
 void choose_grid(const lm_handle* h, int64_t batch, int tiles, int* group, int* n_groups) {
@@ -325,6 +338,15 @@ int lm_kernel_info(const lm_handle* h, int32_t* n_sm, int32_t* ctas_per_sm, int3
   return 0;
 }
 
+const char* lm_kernel_name(const lm_handle* h, int64_t batch, int64_t n_samples) {
+  if (!h) return "";
+  const int64_t n_frames = frames_for(h->cfg, n_samples);
+  if (use_tf(h, batch, n_frames, true))
+    return h->cfg.n_mels == 80 ? (n_frames == 3000 ? "lm::logmel_tf_kernel<80, 3000>" : "lm::logmel_tf_kernel<80, 0>")
+                               : (n_frames == 3000 ? "lm::logmel_tf_kernel<128, 3000>" : "lm::logmel_tf_kernel<128, 0>");
+  return h->tiled_name.c_str();
+}
+
 int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_stride, int64_t n_samples,
                const int32_t* d_lengths, float* d_out, float* d_clip_max, void* d_scratch,
                size_t scratch_bytes, void* stream) {
@@ -386,9 +408,8 @@ int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_st
     a.gmax = reinterpret_cast<float*>(d_scratch) + ((batch + 3) / 4) * 4;
   }
   int rc;
-  const int64_t tf_tiles = (n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F;
-  if (h->tf && a.tma_ok && batch >= h->tf_min_batch && tf_tiles <= lm::kTfMaxTiles) {
-    a.tiles_per_clip = (int)tf_tiles;
+  if (use_tf(h, batch, n_frames, a.tma_ok != 0)) {
+    a.tiles_per_clip = (int)((n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F);
     rc = h->tf->launch(a, st);
   } else {
     if (norm) CUDA_TRY(cudaMemsetAsync(a.gcnt, 0, (size_t)batch * sizeof(int), st));

@@ -11,30 +11,33 @@
 //             odd, so the 8 lanes of a quarter-warp phase hit 8 different 16-byte banks) and runs
 //             the windowed real DFT-20 of two adjacent columns at a time, packed in f32x2
 //             (FFMA2/FADD2; the LDS.128 result registers ARE the packed pairs).  Window samples
-//             and twiddles are the same for every lane => uniform-register operands (LDCU), no
-//             shared-memory constants.
+//             and twiddles are the same for every lane: warp-uniform LDS.128 from a shared-memory
+//             copy of the table (uniform-register loads, LDCU, were tried first: ptxas places them
+//             a few instructions before their use and every FFMA2 waits on the short scoreboard,
+//             5.65 vs 4.40 ms per 4096 clips).
 //   transpose the 420 inter-stage values of the frame are parked in TENSOR MEMORY, used as
-//             lane-private scratch: warp w of the CTA owns TMEM lanes 32w..32w+31, lane = frame,
-//             column = (row k1, re/im, column b).  tcgen05.st / tcgen05.ld with the 32x32b shape
-//             are exactly "each thread writes / reads N consecutive words of its own lane", so the
-//             column -> row transpose costs no shared-memory bandwidth, no swizzle and no barrier
-//             (tools/microbench/tmem_scratch.cu: no MMA is needed to use TMEM; 220-350 B/cycle/SM).
-//   stage 2   per row k1: 40 values back from TMEM, complex DFT-20 + |X|^2 in scalar FP32 (same
-//             FMA-pipe time as the packed form), power written over the row in place.
+//             lane-private scratch: the warps of TMEM lane quadrant q own lanes 32q..32q+31, lane =
+//             frame, column = (row pair, column b, re/im).  tcgen05.st / tcgen05.ld with the 32x32b
+//             shape are exactly "each thread writes / reads N consecutive words of its own lane", so
+//             the column -> row transpose costs no shared-memory bandwidth, no swizzle and no CTA
+//             barrier (tools/microbench/tmem_scratch.cu: no MMA is needed to use TMEM).
+//   stage 2   per ROW PAIR (k, k'): 80 values back from TMEM, two complex DFT-20 + |X|^2 as one
+//             packed codelet (the TMEM column order makes (Y_k[b], Y_k'[b]) adjacent registers),
+//             powers written over the pair in place; row 0 (real input) alone in scalar FP32.
 //   mel       straight-line banded projection generated for the two Whisper banks
-//             (tf_mel_gen.cuh): weights are constant-bank operands, the n_mels sums of the frame
-//             live in registers; then log2 * scale, running clip max / tile min, (S+4)/4 and a
+//             (tf_mel_gen.cuh): weights are immediates of the FFMAs, the sums of the frame live in
+//             registers; then log2, running clip max / tile min (FMNMX3), (S+4)/4 as one FFMA and a
 //             store that is coalesced across the warp (lane = consecutive frame).
 //
 // Two warps share a tile of 32 frames (and a TMEM lane quadrant, which one frame's 420 values nearly
-// fill): both have lane = frame, role A takes column pairs 0-4 / rows 0-4,10 / the low filters, role B
-// column pairs 5-9 / rows 5-9 / the high filters, and they meet at three 64-thread named barriers
-// per tile.  The two warps sit on the same SM sub-partition, so whenever one waits for shared or
-// tensor memory the other issues.  A pair walks a whole clip, so the Whisper max - 8 rule needs no
-// inter-CTA agreement (the per-tile minimum decides which tiles are revisited, as in the other
-// kernels).  The waveform tile of the next 32 frames is fetched with cp.async (16-byte chunks,
-// coalesced) while stage 2 / mel of the current one run.  Grid: one CTA of 4 pairs per SM (the CTA
-// owns all 512 TMEM columns).
+// fill): both have lane = frame, role A takes column pairs 0-4 / row 0 and row pairs 0-1 / the low
+// filters, role B column pairs 5-9 / row pairs 2-4 / the high filters, and they meet at three
+// 64-thread named barriers per tile.  The two warps sit on the same SM sub-partition, so whenever
+// one waits for shared or tensor memory the other issues.  A pair walks a whole clip, so the
+// Whisper max - 8 rule needs no inter-CTA agreement (the per-tile minimum decides which tiles are
+// revisited, as in the other kernels).  The waveform tile of the next 32 frames is fetched with
+// cp.async (16-byte chunks, coalesced) in groups between the stage-2 codelets of the current one.
+// Grid: one CTA of 4 pairs per SM (the CTA owns all 512 TMEM columns), no cooperative launch.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -86,6 +89,19 @@ __device__ __forceinline__ void tm_st4(uint32_t addr, float a, float b, float c,
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
+__device__ __forceinline__ void tm_st8v(uint32_t addr, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "f"(a), "f"(b),
+               "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h)
+               : "memory");
+}
+__device__ __forceinline__ void tm_st32(uint32_t addr, const float* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(addr),
+      LM_TM_R4(r, 0), LM_TM_R4(r, 4), LM_TM_R4(r, 8), LM_TM_R4(r, 12), LM_TM_R4(r, 16), LM_TM_R4(r, 20), LM_TM_R4(r, 24),
+      LM_TM_R4(r, 28)
+      : "memory");
+}
 __device__ __forceinline__ void tm_st8(uint32_t addr, const float* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr),
                LM_TM_R4(r, 0), LM_TM_R4(r, 4)
@@ -124,6 +140,18 @@ __device__ __forceinline__ void tm_ld32(uint32_t addr, float* r) {
       : "r"(addr)
       : "memory");
 }
+__device__ __forceinline__ void tm_ld64(uint32_t addr, float* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, "
+      "%38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, "
+      "%60, %61, %62, %63}, [%64];"
+      : LM_TM_W4(r, 0), LM_TM_W4(r, 4), LM_TM_W4(r, 8), LM_TM_W4(r, 12), LM_TM_W4(r, 16), LM_TM_W4(r, 20),
+        LM_TM_W4(r, 24), LM_TM_W4(r, 28), LM_TM_W4(r, 32), LM_TM_W4(r, 36), LM_TM_W4(r, 40), LM_TM_W4(r, 44),
+        LM_TM_W4(r, 48), LM_TM_W4(r, 52), LM_TM_W4(r, 56), LM_TM_W4(r, 60)
+      : "r"(addr)
+      : "memory");
+}
 __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -133,14 +161,16 @@ __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// TMEM columns of a frame.  Row 0 of Y is real: 20 columns, column b at [b].  Rows k1 = 1..10 take 40
-// columns each; a stage-1 codelet produces the two adjacent columns (b, b + 1) = column pair cp
-// as packed pairs (re b, re b+1) and (im b, im b+1), which go out with ONE 4-column store:
-//   [base(k1) + 4 cp + {0, 1, 2, 3}] = re(2cp), re(2cp+1), im(2cp), im(2cp+1)
-// Stage 2 reads the 40 columns of a row with two loads; the order is a compile-time renaming.
-__device__ __forceinline__ constexpr int tf_row_base(int k1) { return k1 == 0 ? 0 : 20 + 40 * (k1 - 1); }
-__device__ __forceinline__ constexpr int tf_re(int b) { return 4 * (b / 2) + (b & 1); }
-__device__ __forceinline__ constexpr int tf_im(int b) { return 4 * (b / 2) + 2 + (b & 1); }
+// TMEM columns of a frame (420 of the 512).  Row 0 of Y is real: 20 columns, column b at [b].  Rows
+// k1 = 1..10 are kept as the five ROW PAIRS q = (2q+1, 2q+2), 80 columns each, interleaved so that
+// stage 2 can run both rows of a pair in one packed (f32x2) codelet:
+//   [pair_base(q) + 4 b + {0, 1, 2, 3}] = re_k(b), re_k'(b), im_k(b), im_k'(b)        k = 2q+1, k' = 2q+2
+// A load of the 80 columns returns (re_k(b), re_k'(b)) and (im_k(b), im_k'(b)) as adjacent registers
+// = the packed operands.  A stage-1 codelet holds (column b, column b+1) packed instead, so it
+// assembles the eight columns of (b, b+1) x (k, k') x (re, im) for one 8-column store (a 2 x 2
+// register transpose per value pair: two MOVs on the otherwise idle ALU pipe).
+// Stage 2 writes the powers back in place: [pair_base(q) + 2 j + {0, 1}] = P_k(j), P_k'(j).
+__device__ __forceinline__ constexpr int tf_pair_base(int q) { return 20 + 80 * q; }
 
 // one stage-1 codelet: columns (2 CP, 2 CP + 1) of this lane's frame; every table offset and
 // every tensor-memory column is a compile-time constant (uniform-register operands, no index math)
@@ -164,7 +194,11 @@ __device__ __forceinline__ void tf_stage1_pair(const TabRef& tab, const float4 (
   stage1_r20p<f32x2>(x, w, twr, twi, ntwi, nw, ntwr, yr, yi);
   tm_st2(tm + 2 * CP, vlo(yr[0]), vhi(yr[0]));
 #pragma unroll
-  for (int k = 1; k <= 10; ++k) tm_st4(tm + tf_row_base(k) + 4 * CP, vlo(yr[k]), vhi(yr[k]), vlo(yi[k]), vhi(yi[k]));
+  for (int q = 0; q < 5; ++q) {
+    const int k = 2 * q + 1, k2 = 2 * q + 2;
+    tm_st8v(tm + tf_pair_base(q) + 8 * CP, vlo(yr[k]), vlo(yr[k2]), vlo(yi[k]), vlo(yi[k2]), vhi(yr[k]), vhi(yr[k2]),
+            vhi(yi[k]), vhi(yi[k2]));
+  }
 }
 
 __device__ __forceinline__ void tf_load_group(const float* mine, int g4, float4 (&x4)[20]) {
@@ -175,20 +209,29 @@ __device__ __forceinline__ void tf_load_group(const float* mine, int g4, float4 
   }
 }
 
-// one row k1 = 1..9 of stage 2: 40 columns in, complex DFT-20, |X|^2, 20 columns out (in place)
-__device__ __forceinline__ void tf_stage2_row(uint32_t base) {
-  float y[40], yr[20], yi[20], p[20];
-  tm_ld32(base, y);
-  tm_ld8(base + 32, y + 32);
+// one row pair of stage 2: 80 columns in, two complex DFT-20 + |X|^2 as one packed codelet, 40 columns
+// out (in place).  For the pair (9, 10) row 10 runs through the general codelet as well; its outputs
+// j >= 10 repeat bins it already has and are not used.
+__device__ __forceinline__ void tf_stage2_pair(uint32_t base) {
+  float y[80];
+  tm_ld64(base, y);
+  tm_ld16(base + 64, y + 64);
   tm_wait_ld();
+  f32x2 yr[20], yi[20], p[20];
 #pragma unroll
   for (int b = 0; b < 20; ++b) {
-    yr[b] = y[tf_re(b)];
-    yi[b] = y[tf_im(b)];
+    yr[b] = vpack(y[4 * b], y[4 * b + 1]);
+    yi[b] = vpack(y[4 * b + 2], y[4 * b + 3]);
   }
-  stage2_c20<float>(yr, yi, p);
-  tm_st16(base, p);
-  tm_st4(base + 16, p[16], p[17], p[18], p[19]);
+  stage2_c20<f32x2>(yr, yi, p);
+  float o[40];
+#pragma unroll
+  for (int j = 0; j < 20; ++j) {
+    o[2 * j] = vlo(p[j]);
+    o[2 * j + 1] = vhi(p[j]);
+  }
+  tm_st32(base, o);
+  tm_st8(base + 32, o + 32);
 }
 
 __device__ __forceinline__ void pair_sync(int pair) {     // the two warps of a pair: named barrier 1 + pair
@@ -204,35 +247,27 @@ __device__ __forceinline__ void tf_mel_store(uint32_t tm, float* op, long long o
   float acc[P::MAXHALF];
 #pragma unroll
   for (int m = 0; m < P::MAXHALF; ++m) acc[m] = 0.0f;
-  float pa[20], pb[20];
-#pragma unroll
-  for (int j = 0; j < 20; ++j) pa[j] = pb[j] = 0.0f;
-  tm_ld8(tm, pa);
-  tm_ld4(tm + 8, pa + 8);
+  float p0[12], pa[40], pb[40];
+  tm_ld8(tm, p0);
+  tm_ld4(tm + 8, p0 + 8);
+  tm_ld32(tm + tf_pair_base(0), pa);
+  tm_ld8(tm + tf_pair_base(0) + 32, pa + 32);
   tm_wait_ld();
-  // rows alternate between two register sets: the next row is on its way while this one is used
-#define LM_TF_ROW(K1, CUR, NXT)                                          \
-  if (K1 < 9) {                                                          \
-    tm_ld16(tm + tf_row_base(K1 + 1), NXT);                              \
-    tm_ld4(tm + tf_row_base(K1 + 1) + 16, NXT + 16);                     \
-  } else if (K1 == 9) {                                                  \
-    tm_ld8(tm + tf_row_base(10), NXT);                                   \
-    tm_ld4(tm + tf_row_base(10) + 8, NXT + 8);                           \
+  tf_mel_row0<NM, R>(p0, acc);
+  // row pairs alternate between two register sets: the next pair is on its way while this one is used
+#define LM_TF_PAIR(Q, CUR, NXT)                                          \
+  if (Q < 4) {                                                           \
+    tm_ld32(tm + tf_pair_base(Q + 1), NXT);                              \
+    tm_ld8(tm + tf_pair_base(Q + 1) + 32, NXT + 32);                     \
   }                                                                      \
-  tf_mel_row<NM, K1, R>(CUR, acc);                                       \
-  if (K1 < 10) tm_wait_ld();
-  LM_TF_ROW(0, pa, pb)
-  LM_TF_ROW(1, pb, pa)
-  LM_TF_ROW(2, pa, pb)
-  LM_TF_ROW(3, pb, pa)
-  LM_TF_ROW(4, pa, pb)
-  LM_TF_ROW(5, pb, pa)
-  LM_TF_ROW(6, pa, pb)
-  LM_TF_ROW(7, pb, pa)
-  LM_TF_ROW(8, pa, pb)
-  LM_TF_ROW(9, pb, pa)
-  LM_TF_ROW(10, pa, pb)
-#undef LM_TF_ROW
+  tf_mel_pair<NM, Q, R>(CUR, acc);                                       \
+  if (Q < 4) tm_wait_ld();
+  LM_TF_PAIR(0, pa, pb)
+  LM_TF_PAIR(1, pb, pa)
+  LM_TF_PAIR(2, pa, pb)
+  LM_TF_PAIR(3, pb, pa)
+  LM_TF_PAIR(4, pa, pb)
+#undef LM_TF_PAIR
   // running maximum / tile minimum of log2(mel): four independent chains of 3-input min / max
   float hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
   op += M0 * ostep;
@@ -256,15 +291,13 @@ __global__ void __launch_bounds__(TfGeo::THREADS, 1)
 logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
   using G = TfGeo;
   using MP = TfMelPattern<NM>;
-#ifdef LM_TF_SMEM_CONST
-  // stage-1 constants as shared-memory operands (warp-uniform LDS) instead of uniform-register loads
+  // Stage-1 constants as shared-memory operands (warp-uniform LDS.128, ~2 LSU cycles each) instead of
+  // uniform-register loads: ptxas places an LDCU only a few instructions before its first use and
+  // every FFMA2 then waits ~30 cycles on the short scoreboard (measured: 5.65 vs 4.40 ms per 4096 clips).
   __shared__ TfTables s_tab;
   for (int i = threadIdx.x; i < (int)(sizeof(TfTables) / 8); i += blockDim.x)
     reinterpret_cast<unsigned long long*>(&s_tab)[i] = reinterpret_cast<const unsigned long long*>(&ctab)[i];
   const TfTables& tab = s_tab;
-#else
-  const TfTables& tab = ctab;
-#endif
   static_assert(MP::M0 % 2 == 0 && NM % 2 == 0, "the epilogue walks filters two at a time");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_tmem;
@@ -393,12 +426,15 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
       if (tn < T) fetch_begin(tn);   // the copies themselves go out between the stage-2 rows
 
       // ================= stage 2: rows of Y -> |X|^2, in place =================
+      // (role A: row 0 and row pairs 0, 1; role B: row pairs 2, 3, 4; the cp.async groups of the next
+      //  tile go out in between)
       if (role == 0) {
         {
           float yr[20], p[12], pr[11];
           tm_ld16(tm, yr);
           tm_ld4(tm + 16, yr + 16);
           tm_wait_ld();
+          fetch_rows4(0);
           stage2_r20_half<float>(yr, pr);
 #pragma unroll
           for (int j = 0; j < 11; ++j) p[j] = pr[j];
@@ -407,34 +443,19 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
           tm_st4(tm + 8, p[8], p[9], p[10], p[11]);
         }
 #pragma unroll 1
-        for (int k1 = 1; k1 <= 4; ++k1) {
-          fetch_rows4(k1 - 1);
-          tf_stage2_row(tm + (uint32_t)(20 + 40 * (k1 - 1)));
+        for (int q = 0; q < 2; ++q) {
+          fetch_rows4(1 + q);
+          tf_stage2_pair(tm + (uint32_t)tf_pair_base(q));
         }
-        {
-          const uint32_t base = tm + (uint32_t)tf_row_base(10);
-          float y[40], yr[20], yi[20], p[12], ph[10];
-          tm_ld32(base, y);
-          tm_ld8(base + 32, y + 32);
-          tm_wait_ld();
-#pragma unroll
-          for (int b = 0; b < 20; ++b) {
-            yr[b] = y[tf_re(b)];
-            yi[b] = y[tf_im(b)];
-          }
-          stage2_c20_half<float>(yr, yi, ph);
-#pragma unroll
-          for (int j = 0; j < 10; ++j) p[j] = ph[j];
-          p[10] = p[11] = 0.0f;
-          tm_st8(base, p);
-          tm_st4(base + 8, p[8], p[9], p[10], p[11]);
-        }
+        fetch_rows4(3);
       } else {
 #pragma unroll 1
-        for (int k1 = 5; k1 <= 9; ++k1) {
-          fetch_rows4(k1 - 5);
-          tf_stage2_row(tm + (uint32_t)(20 + 40 * (k1 - 1)));
+        for (int q = 2; q < 5; ++q) {
+          fetch_rows4(q - 2);
+          tf_stage2_pair(tm + (uint32_t)tf_pair_base(q));
         }
+        fetch_rows4(3);
+        fetch_rows4(4);
       }
       cp_async_commit();
       tm_wait_st();
@@ -447,9 +468,9 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
         if (role == 0) tf_mel_store<NM, 0>(tm, op, (long long)n_frames, q_scale, hi, lo);
         else tf_mel_store<NM, 1>(tm, op, (long long)n_frames, q_scale, hi, lo);
         rmax = fmaxf(rmax, hi);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        if (lane == 0) s_tmin[pair][t][role] = lo * log_scale;
+        float wlo;                 // minimum over the warp in one instruction (NaN if any lane has one)
+        asm volatile("redux.sync.min.NaN.f32 %0, %1, 0xffffffff;" : "=f"(wlo) : "f"(lo));
+        if (lane == 0) s_tmin[pair][t][role] = wlo * log_scale;
       }
       t = tn;
     }

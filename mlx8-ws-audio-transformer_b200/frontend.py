@@ -66,6 +66,10 @@ class LogMelFrontend:
         keys = ("n_sm", "ctas_per_sm", "smem_bytes", "threads", "frames_per_tile")
         return {k: int(x.value) for k, x in zip(keys, v)}
 
+    def kernel_name(self, batch: int, n_samples: int) -> str:
+        """the kernel ``forward`` launches for this batch (as ncu prints it)"""
+        return self._lib.lm_kernel_name(self._h, int(batch), int(n_samples)).decode()
+
     def _scratch_for(self, batch: int):
         import torch
 

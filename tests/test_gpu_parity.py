@@ -43,7 +43,7 @@ def fronts():
 # golden vectors (outputs of the live HF / torchaudio calls, committed under tests/golden)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nm", [80, 128])
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_whisper_short_golden(golden_whisper_short, fronts, nm, variant):
     g = golden_whisper_short
     names = [str(n) for n in g["names"]]
@@ -77,7 +77,7 @@ def test_whisper_dropin_call_golden(golden_whisper_short, nm):
 
 
 @pytest.mark.parametrize("nm", [80, 128])
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_whisper_30s_golden(golden_whisper_30s, fronts, nm, variant):
     g = golden_whisper_30s
     x = np.concatenate([synth.gaussian_clips(3, seed=0), synth.midi_piano_clips(2, seed=0)[0],
@@ -133,14 +133,18 @@ def test_whisper_vs_oracle_mixed_batch(fronts, nm):
              synth.chirp_clip(), (synth.gaussian_clips(1, n, seed=23)[0] * 1e-4).astype(np.float32), np.full(n, 0.3, np.float32)]
     x = np.stack(clips)                                             # odd batch of 11
     ref = O.whisper_logmel(x, n_mels=nm)
-    for variant in (1, 2):
+    # every kernel: 0 = warp-specialised CTA (what a batch of 11 takes by default), 1 / 2 = phase-synchronous
+    # CTA, 3 = thread-per-frame kernel (what batches >= 4 clips per SM take by default)
+    for variant in (0, 1, 2, 3):
         got = fronts(nm, variant).forward(torch.from_numpy(x).cuda())
         for i in range(len(clips)):
             _assert_parity(got[i], ref[i], f"clip{i} v{variant}")
+        assert np.abs(got[5].cpu().numpy() + 1.5).max() < 1e-6      # the all-zero clip: exactly -1.5
 
 
-def test_lengths_truncation_and_short_clips(fronts):
-    fe = fronts(80, 2)
+@pytest.mark.parametrize("variant", [2, 3])
+def test_lengths_truncation_and_short_clips(fronts, variant):
+    fe = fronts(80, variant)
     n = 480000
     x = synth.gaussian_clips(4, n + 1000, seed=31)                  # longer than the container
     lengths = np.array([n + 1000, 1, 399, 250001], np.int32)
@@ -157,9 +161,11 @@ def test_lengths_truncation_and_short_clips(fronts):
         _assert_parity(fe.forward(torch.from_numpy(w).cuda()), O.whisper_logmel(w, n_mels=80, n_samples=L), f"L={L}")
 
 
-@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("variant", [0, 2, 3])
 def test_batch_position_group_size_and_paths_are_bit_identical(fronts, variant):
-    """A clip's features do not depend on batch size, batch position, CTA grouping or entry point."""
+    """A clip's features do not depend on batch size, batch position, CTA grouping or entry point
+    (within one kernel: variant 0 keeps batches this small on the CTA-tiled kernel, variant 3 forces
+    the thread-per-frame kernel for all of them)."""
     fe = fronts(128, variant)
     x = torch.from_numpy(synth.gaussian_clips(40, seed=41)).cuda()
     full = fe.forward(x)
@@ -182,9 +188,12 @@ def test_batch_position_group_size_and_paths_are_bit_identical(fronts, variant):
 
 
 def test_full_size_properties():
-    """Config-2 shape at a size the GPU test can afford: 592 x 30 s clips, 128 mels."""
+    """Config-2 shape at a size the GPU test can afford: 1184 x 30 s clips, 128 mels -- the default
+    dispatch sends this batch (and its 592-clip shard below) to the thread-per-frame kernel."""
     fe = LogMelFrontend(400, 160, O.slaney_mel_filter_bank(201, 128), N.LOG10_CLAMP_WHISPER_NORM, 1e-10, True)
-    B = 592
+    B = 1184
+    assert "logmel_tf_kernel<128, 3000>" in fe.kernel_name(B, 480000)
+    assert "logmel_ws_kernel" in fe.kernel_name(8, 480000)
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(B, 480000, generator=g, device="cuda") * 0.1
     x[17] = 0.0
@@ -201,17 +210,21 @@ def test_full_size_properties():
     d = (y[100] - z[0])
     keep = (z[0] > z[0].min() + 1e-3) & (y[100] > y[100].min() + 1e-3)
     assert (d[keep] - 2 * np.log10(50.0) / 4).abs().max() < 1e-4
-    sub = [0, 17, 100, 311, 591]
+    sub = [0, 17, 100, 311, 591, 1183]
     ref = O.whisper_logmel(x[sub].cpu().numpy(), n_mels=128)
     _assert_parity(y[sub], ref, "subset")
-    assert torch.equal(fe.forward(x[300:]), y[300:])               # contiguous shard == slice of the whole
+    assert torch.equal(fe.forward(x[592:]), y[592:])               # contiguous shard == slice of the whole
+    # a shard small enough for the CTA-tiled kernel agrees to float32 rounding, not bit for bit
+    assert (fe.forward(x[:40]) - y[:40]).abs().max() < 2e-6
 
 
 @pytest.mark.parametrize("nm", [80, 128])
-def test_clamp_everywhere_one_cta_per_clip(nm):
-    """> 148 clips (every CTA owns whole clips) whose quiet parts lie > 80 dB under one loud burst:
-    every tile is revisited by the max-8 pass after the clip maximum is known."""
-    fe = LogMelFrontend(400, 160, O.slaney_mel_filter_bank(201, nm), N.LOG10_CLAMP_WHISPER_NORM, 1e-10, True)
+@pytest.mark.parametrize("variant", [0, 3])
+def test_clamp_everywhere_one_cta_per_clip(nm, variant):
+    """> 148 clips (every CTA / warp pair owns whole clips) whose quiet parts lie > 80 dB under one loud
+    burst: every tile is revisited by the max-8 pass after the clip maximum is known."""
+    fe = LogMelFrontend(400, 160, O.slaney_mel_filter_bank(201, nm), N.LOG10_CLAMP_WHISPER_NORM, 1e-10, True,
+                        variant=variant)
     B = 300
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.randn(B, 480000, generator=g, device="cuda") * 1e-5

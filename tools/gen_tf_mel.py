@@ -44,20 +44,19 @@ def row_bins(k1: int):
 
 
 EPILOGUE_COST = 5      # instructions per finished filter (log2, fma, store, 2 x min/max share) vs 1 per weight
-STAGE2_BIAS = 56       # role A carries ~56 more stage-2 instructions per tile than role B (rows 0-4,10 vs 5-9)
+STAGE2_BIAS = -170     # role A (row 0, row pairs 0-1) carries ~170 FEWER stage-2 instructions per tile than role B (pairs 2-4)
 
 
 def split_point(fb, nm: int) -> int:
-    """first filter of role B: both warps of a pair should get the same mel + epilogue work"""
+    """first filter of role B: both warps of a pair should get the same stage-2 + mel + epilogue work"""
     nnz = [(fb[:, m] != 0).sum() for m in range(nm)]
     cost = [int(n) + EPILOGUE_COST for n in nnz]
-    total = sum(cost)
-    best, best_d = 1, None
-    for m0 in range(1, nm):
+    best, best_d = 2, None
+    for m0 in range(2, nm - 1, 2):      # even: the epilogue walks filters two at a time
         d = abs((sum(cost[:m0]) + STAGE2_BIAS) - sum(cost[m0:]))
         if best_d is None or d < best_d:
             best, best_d = m0, d
-    return best & ~1        # even: the epilogue walks filters two at a time
+    return best
 
 
 def emit_bank(nm: int) -> str:
@@ -68,16 +67,31 @@ def emit_bank(nm: int) -> str:
     lines = []
     for role in (0, 1):
         lo, hi = (0, m0) if role == 0 else (m0, nm)
-        for k1 in range(11):
+
+        def fmas(src, k):
+            out = []
+            for m in range(lo, hi):
+                if fb[k, m] != 0.0:
+                    order.append((k, m))
+                    out.append(f"  acc[{m - lo}] = __builtin_fmaf({src}, {float(fb[k, m]):.9e}f, acc[{m - lo}]);")
+            return out
+
+        # row 0: p[j] = power of bin 20 j
+        body = []
+        for j, k in enumerate(row_bins(0)):
+            body += fmas(f"p[{j}]", k)
+        lines.append(f"template <> LM_D void tf_mel_row0<{nm}, {role}>(const float (&p)[12], "
+                     f"float (&acc)[TfMelPattern<{nm}>::MAXHALF]) {{   // {len(body)} weights")
+        lines += body
+        lines.append("}")
+        # row pair q = rows (2q+1, 2q+2): pp[2j] = row 2q+1 output j, pp[2j+1] = row 2q+2 output j
+        for q in range(5):
             body = []
-            for j, k in enumerate(row_bins(k1)):
-                for m in range(lo, hi):
-                    if fb[k, m] != 0.0:
-                        order.append((k, m))
-                        body.append(f"  acc[{m - lo}] = __builtin_fmaf(p[{j}], {float(fb[k, m]):.9e}f, acc[{m - lo}]);")
-            n = len(row_bins(k1))
-            lines.append(f"template <> LM_D void tf_mel_row<{nm}, {k1}, {role}>(const float (&p)[20], "
-                         f"float (&acc)[TfMelPattern<{nm}>::MAXHALF]) {{   // {n} bins, {len(body)} weights")
+            for half, k1 in enumerate((2 * q + 1, 2 * q + 2)):
+                for j, k in enumerate(row_bins(k1)):
+                    body += fmas(f"pp[{2 * j + half}]", k)
+            lines.append(f"template <> LM_D void tf_mel_pair<{nm}, {q}, {role}>(const float (&pp)[40], "
+                         f"float (&acc)[TfMelPattern<{nm}>::MAXHALF]) {{   // rows {2 * q + 1}, {2 * q + 2}: {len(body)} weights")
             lines += body
             lines.append("}")
     assert sorted(order) == sorted(nz), "every non-zero weight is used exactly once"
@@ -102,9 +116,11 @@ def emit_bank(nm: int) -> str:
 
 HEADER = '''// GENERATED by tools/gen_tf_mel.py -- do not edit by hand.
 //
-// Straight-line banded mel projection for logmel_tf_kernel.cuh: tf_mel_row<NM, K1, R>(p, acc) adds
-// the contributions of stage-2 row K1 (p[j] = |X|^2 of bin K1 + 20 j, folded) to the per-frame sums
-// of the filters of role R (the two warps that share a frame tile split the filters at
+// Straight-line banded mel projection for logmel_tf_kernel.cuh.  Stage 2 leaves the power spectrum of
+// a frame in tensor memory row by row: row 0 alone (p[j] = |X|^2 of bin 20 j), rows (2q+1, 2q+2) as
+// packed pairs (pp[2j], pp[2j+1] = output j of the two rows; output j of row k1 is bin k1 + 20 j,
+// folded to <= 200).  tf_mel_row0 / tf_mel_pair<NM, Q, R> add those contributions to the per-frame
+// sums of the filters of role R (the two warps that share a frame tile split the filters at
 // TfMelPattern<NM>::M0; acc is indexed from the role's first filter).  The weights are literals (float32 images in TfMelPattern<NM>::bits, checked against
 // lm_config.fbank by lm_create).
 #pragma once
@@ -114,7 +130,8 @@ namespace lm {
 
 constexpr int kTfMaxNnz = 400;
 template <int NM> struct TfMelPattern;
-template <int NM, int K1, int R> LM_D void tf_mel_row(const float (&p)[20], float (&acc)[TfMelPattern<NM>::MAXHALF]);
+template <int NM, int R> LM_D void tf_mel_row0(const float (&p)[12], float (&acc)[TfMelPattern<NM>::MAXHALF]);
+template <int NM, int Q, int R> LM_D void tf_mel_pair(const float (&pp)[40], float (&acc)[TfMelPattern<NM>::MAXHALF]);
 '''
 
 

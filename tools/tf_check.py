@@ -94,11 +94,25 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-tiled", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="tf vs tiled kernel over batch sizes (dispatch threshold)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     ok = True
     if not args.no_parity:
         ok = parity()
+    if args.sweep:
+        g = torch.Generator(device="cuda").manual_seed(0)
+        x = torch.randn(2400, 480000, generator=g, device="cuda") * 0.1
+        out = torch.empty(2400, args.mels, 3000, device="cuda")
+        f3 = front(args.mels, 3)
+        os.environ["LM_TF_MIN_BATCH"] = "1000000000"
+        f0 = front(args.mels, 0)
+        os.environ.pop("LM_TF_MIN_BATCH")
+        for b in (1, 8, 32, 74, 148, 222, 296, 444, 592, 888, 1184, 1776, 2368):
+            t3 = timeit(f3, x[:b], out[:b], args.iters)[0]
+            t0 = timeit(f0, x[:b], out[:b], args.iters)[0]
+            print(f"batch {b:5d}: thread-per-frame {t3 * 1e3:8.1f} us   CTA-tiled {t0 * 1e3:8.1f} us   ratio {t0 / t3:.2f}")
+        sys.exit(0)
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(args.clips, 480000, generator=g, device="cuda") * 0.1
     out = torch.empty(args.clips, args.mels, 3000, device="cuda")
