@@ -110,6 +110,21 @@ int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_st
                int64_t n_samples, const int32_t* d_lengths, float* d_out, float* d_clip_max,
                void* d_scratch, size_t scratch_bytes, void* stream);
 
+/* Fused 16-bit PCM ingest: the same operator for clips that are still what a WAV file
+ * holds -- int16 frames of `channels` (1 or 2) interleaved channels -- so that the s16 -> float32
+ * conversion of torchaudio.load (/root/reference/AB/wavToWhisper.py:52, AB/memoToWav.py:19 writes s16
+ * mono) and the stereo -> mono mean of /root/reference/.charles/spectrogram.py:147-148 happen in the
+ * kernel's tile loader: sample = sum_c pcm[frame][c] / (32768 * channels), bit-identical to the float
+ * path on the converted waveform.  clip_stride, n_samples and d_lengths count FRAMES.  Halves (mono) the
+ * bytes read from HBM / sent over PCIe.  Every clip should start 16-byte aligned
+ * (clip_stride * channels % 8 == 0) for the vectorised loader; other layouts are read sample by sample.
+ */
+int lm_forward_pcm16(lm_handle* h, const int16_t* d_pcm, int32_t channels, int64_t batch,
+                     int64_t clip_stride, int64_t n_samples, const int32_t* d_lengths, float* d_out,
+                     float* d_clip_max, void* d_scratch, size_t scratch_bytes, void* stream);
+int lm_forward_host_pcm16(lm_handle* h, const int16_t* h_pcm, int32_t channels, int64_t batch,
+                          int64_t clip_stride, int64_t n_samples, const int32_t* h_lengths, float* h_out);
+
 /* Host-buffer forward: the same operator for HOST waveforms and HOST features.  The batch is
  * cut into chunks that are copied to the device, transformed and copied back on three
  * streams so that H2D, compute and D2H overlap; device staging buffers belong to the handle

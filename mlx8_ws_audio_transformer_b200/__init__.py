@@ -1,13 +1,40 @@
-"""Importable name of the package that lives in ``mlx8-ws-audio-transformer_b200/``.
+"""B200-native log-mel feature frontend (drop-in for the reference's feature-extraction call).
 
-The product directory carries the repository's name, which is not a valid Python identifier;
-this shim makes ``import mlx8_ws_audio_transformer_b200`` resolve to it without symlinks.
+Public surface:
+
+* :class:`LogMelWhisperFeatureExtractor` -- ``WhisperFeatureExtractor`` replacement
+  (``AB/fineTune.py:88``, ``AB/wavToWhisper.py:55``, ``.charles/music2midi/model.py:100-104``);
+* :class:`MelSpectrogram` / :class:`LogMelSpectrogram` -- ``torchaudio.transforms.MelSpectrogram``
+  replacement (``.charles/spectrogram.py:79-87,161-162``);
+* :class:`LogMelFrontend` -- the raw operator over device or host buffers;
+* :class:`ShardedFrontend`, :func:`shard_bounds` -- clip sharding across ranks.
+
+Heavy imports (torch, transformers) happen on first attribute access, not at package import.
 """
-import os as _os
+from __future__ import annotations
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
-                      "mlx8-ws-audio-transformer_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
-del _os, _f
+__all__ = [
+    "LogMelFrontend", "LogMelWhisperFeatureExtractor", "MelSpectrogram", "LogMelSpectrogram",
+    "ShardedFrontend", "shard_bounds", "shard_sizes", "launch_count", "build",
+]
+
+_LAZY = {
+    "LogMelFrontend": ("frontend", "LogMelFrontend"),
+    "launch_count": ("frontend", "launch_count"),
+    "LogMelWhisperFeatureExtractor": ("whisper", "LogMelWhisperFeatureExtractor"),
+    "MelSpectrogram": ("melspec", "MelSpectrogram"),
+    "LogMelSpectrogram": ("melspec", "LogMelSpectrogram"),
+    "ShardedFrontend": ("sharding", "ShardedFrontend"),
+    "shard_bounds": ("sharding", "shard_bounds"),
+    "shard_sizes": ("sharding", "shard_sizes"),
+    "build": ("_native", "build"),
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+
+        mod, attr = _LAZY[name]
+        return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 SYMBOLS = [
     "lm_version", "lm_last_error", "lm_create", "lm_destroy", "lm_num_frames", "lm_scratch_bytes",
     "lm_forward", "lm_forward_host", "lm_host_register", "lm_host_unregister", "lm_launch_count",
-    "lm_kernel_info", "lm_kernel_name",
+    "lm_kernel_info", "lm_kernel_name", "lm_forward_pcm16", "lm_forward_host_pcm16",
 ]
 
 LOG_NONE, LOG10_CLAMP_WHISPER_NORM, LN_PLUS_EPS, LOG10_CLAMP = 0, 1, 2, 3
@@ -105,6 +105,10 @@ def lib() -> ctypes.CDLL:
         L.lm_forward.restype = ctypes.c_int
         L.lm_forward_host.argtypes = [vp, vp, i64, i64, i64, vp, vp]
         L.lm_forward_host.restype = ctypes.c_int
+        L.lm_forward_pcm16.argtypes = [vp, vp, ctypes.c_int32, i64, i64, i64, vp, vp, vp, vp, ctypes.c_size_t, vp]
+        L.lm_forward_pcm16.restype = ctypes.c_int
+        L.lm_forward_host_pcm16.argtypes = [vp, vp, ctypes.c_int32, i64, i64, i64, vp, vp]
+        L.lm_forward_host_pcm16.restype = ctypes.c_int
         L.lm_host_register.argtypes = [vp, ctypes.c_size_t]
         L.lm_host_register.restype = ctypes.c_int
         L.lm_host_unregister.argtypes = [vp]

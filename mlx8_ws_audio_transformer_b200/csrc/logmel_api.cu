@@ -47,6 +47,27 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
   } while (0)
 
+// Makes `device` current for the lifetime of the object and restores the caller's device on every
+// exit path: the library never leaks a cudaSetDevice into the caller (torch reads the same state).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) {
+      err = cudaSetDevice(device);
+      if (err != cudaSuccess) prev = -1;
+    } else if (err == cudaSuccess) {
+      prev = -1;                                   // already current: nothing to restore
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 constexpr int kMaxGroup = 64;
 constexpr int LM_RETRY_PLAIN = -1000;   // internal: the warp-specialised kernel cannot take this filter bank
 
@@ -82,6 +103,7 @@ struct lm_handle {
   std::unique_ptr<TfLauncher> tf;
   long long tf_min_batch = 0;        // smallest batch routed to the thread-per-frame kernel
   std::string tiled_name;            // the CTA-tiled kernel of this handle, as profilers print it
+  int ctas_per_clip = 1;             // CTA-tiled kernels, steady state (tuning knob LM_CTAS_PER_CLIP)
   virtual ~lm_handle() {}
   virtual int launch(const lm::KArgs& a, int grid, cudaStream_t st) = 0;
 };
@@ -154,6 +176,7 @@ int make(lm_handle** out, const lm_config* cfg, const float* window) {
              G::PK, G::WS, cfg->log_mode == LM_LOG_NONE ? 0 : cfg->log_mode == LM_LN_PLUS_EPS ? 2 : cfg->log_mode == LM_LOG10_CLAMP ? 1 : 3);
     h->tiled_name = nm;
   }
+  if (const char* e = std::getenv("LM_CTAS_PER_CLIP")) h->ctas_per_clip = std::max(1, atoi(e));
   h->n_sm = prop.multiProcessorCount;
   h->ctas_per_sm = occ;
   h->smem = smem;
@@ -239,8 +262,7 @@ void choose_grid(const lm_handle* h, int64_t batch, int tiles, int* group, int* 
   // no longer fit the 126 MB L2, so the (pipelined) fix-up of tiles below max-8 reads DRAM; on an
   // input where EVERY tile needs it that costs 5 % (4.37 vs 4.16 ms per 2048 clips).
   // Small batches: spread every clip over as many CTAs as it has tiles.
-  int div = 1;                                   // CTAs per clip in steady state
-  if (const char* e = std::getenv("LM_CTAS_PER_CLIP")) div = std::max(1, atoi(e));   // tuning knob
+  const int div = std::max(1, h->ctas_per_clip);  // CTAs per clip in steady state (LM_CTAS_PER_CLIP, read by lm_create)
   const int steady_groups = std::max(1, h->n_sm / div);
   int g = std::max(1, total / steady_groups);
   if (batch < steady_groups) g = (int)std::min<int64_t>(kMaxGroup, std::max<int64_t>(g, total / std::max<int64_t>(batch, 1)));
@@ -269,7 +291,8 @@ int lm_create(lm_handle** out, const lm_config* cfg) {
   if (e != cudaSuccess || ndev == 0)
     return fail(LM_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(LM_ERR_NO_DEVICE, "device %d out of range", cfg->device);
-  CUDA_TRY(cudaSetDevice(cfg->device));
+  DeviceGuard guard(cfg->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
   std::vector<float> win;
   if (cfg->window) win.assign(cfg->window, cfg->window + cfg->n_fft);
   else if (cfg->n_fft > 0) win = lm::hann_periodic(cfg->n_fft);
@@ -300,7 +323,7 @@ void lm_destroy(lm_handle* h) {
   if (!h) return;
   HostPipe& p = h->pipe;
   if (p.ready) {
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard guard(h->cfg.device);
     for (int i = 0; i < 2; ++i) {
       cudaFree(p.d_wave[i]);
       cudaFree(p.d_out[i]);
@@ -347,12 +370,17 @@ const char* lm_kernel_name(const lm_handle* h, int64_t batch, int64_t n_samples)
   return h->tiled_name.c_str();
 }
 
-int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_stride, int64_t n_samples,
-               const int32_t* d_lengths, float* d_out, float* d_clip_max, void* d_scratch,
-               size_t scratch_bytes, void* stream) {
+}  // extern "C"
+
+namespace {
+// d_wave (float32) or d_pcm (int16, `channels` interleaved channels): exactly one is non-NULL
+int forward_impl(lm_handle* h, const float* d_wave, const int16_t* d_pcm, int channels, int64_t batch, int64_t clip_stride,
+                 int64_t n_samples, const int32_t* d_lengths, float* d_out, float* d_clip_max, void* d_scratch,
+                 size_t scratch_bytes, void* stream) {
   if (!h) return fail(LM_ERR_NULL, "lm_forward: NULL handle");
   if (batch == 0) return 0;
-  if (!d_wave || !d_out) return fail(LM_ERR_NULL, "lm_forward: d_wave and d_out must be non-NULL");
+  if ((!d_wave && !d_pcm) || !d_out) return fail(LM_ERR_NULL, "lm_forward: the waveform and d_out must be non-NULL");
+  if (d_pcm && channels != 1 && channels != 2) return fail(LM_ERR_SHAPE, "channels=%d: 16-bit PCM input is mono or stereo", channels);
   const lm_config& c = h->cfg;
   if (batch < 0 || batch > (1 << 24)) return fail(LM_ERR_SHAPE, "batch=%lld out of range", (long long)batch);
   if (n_samples <= c.n_fft / 2 || n_samples > (1LL << 30))
@@ -369,12 +397,13 @@ int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_st
   if (norm && ((uintptr_t)d_scratch & 15)) return fail(LM_ERR_SCRATCH, "scratch must be 16-byte aligned");
 
   cudaStream_t st = (cudaStream_t)stream;
-  int dev = -1;
-  CUDA_TRY(cudaGetDevice(&dev));
-  if (dev != c.device) CUDA_TRY(cudaSetDevice(c.device));
+  DeviceGuard guard(c.device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
 
   lm::KArgs a{};
   a.wave = d_wave;
+  a.pcm = d_pcm;
+  a.pcm_channels = d_pcm ? channels : 0;
   a.clip_stride = clip_stride;
   a.lengths = d_lengths;
   a.out = d_out;
@@ -397,7 +426,10 @@ int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_st
   a.tiles_per_clip = (int)((n_frames + h->frames_per_tile - 1) / h->frames_per_tile);
   choose_grid(h, batch, a.tiles_per_clip, &a.group, &a.n_groups);
   a.vec_ok = (n_frames % 4 == 0) && (((uintptr_t)d_out & 15) == 0);
-  a.tma_ok = (((uintptr_t)d_wave & 15) == 0) && (clip_stride % 4 == 0);
+  // every clip starts 16-byte aligned (float32: TMA bulk copies / cp.async; PCM: 16-byte vector loads)
+  a.tma_ok = d_pcm ? ((((uintptr_t)d_pcm & 15) == 0) && ((clip_stride * channels) % 8 == 0))
+                   : ((((uintptr_t)d_wave & 15) == 0) && (clip_stride % 4 == 0));
+  const bool aligned = a.tma_ok != 0;
   a.timeline = nullptr;
 #ifdef LM_TIMELINE
   a.timeline = reinterpret_cast<long long*>(d_clip_max);   // debug build: d_clip_max carries the stamp buffer
@@ -408,15 +440,34 @@ int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_st
     a.gmax = reinterpret_cast<float*>(d_scratch) + ((batch + 3) / 4) * 4;
   }
   int rc;
-  if (use_tf(h, batch, n_frames, a.tma_ok != 0)) {
+  if (use_tf(h, batch, n_frames, aligned)) {
     a.tiles_per_clip = (int)((n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F);
     rc = h->tf->launch(a, st);
   } else {
+    if (d_pcm) a.tma_ok = 0;
     if (norm) CUDA_TRY(cudaMemsetAsync(a.gcnt, 0, (size_t)batch * sizeof(int), st));
     rc = h->launch(a, a.group * a.n_groups, st);
   }
-  if (dev != c.device && dev >= 0) cudaSetDevice(dev);
   return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int lm_forward(lm_handle* h, const float* d_wave, int64_t batch, int64_t clip_stride, int64_t n_samples,
+               const int32_t* d_lengths, float* d_out, float* d_clip_max, void* d_scratch,
+               size_t scratch_bytes, void* stream) {
+  if (batch != 0 && !d_wave) return fail(LM_ERR_NULL, "lm_forward: d_wave and d_out must be non-NULL");
+  return forward_impl(h, d_wave, nullptr, 0, batch, clip_stride, n_samples, d_lengths, d_out, d_clip_max, d_scratch,
+                      scratch_bytes, stream);
+}
+
+int lm_forward_pcm16(lm_handle* h, const int16_t* d_pcm, int32_t channels, int64_t batch, int64_t clip_stride,
+                     int64_t n_samples, const int32_t* d_lengths, float* d_out, float* d_clip_max, void* d_scratch,
+                     size_t scratch_bytes, void* stream) {
+  if (batch != 0 && !d_pcm) return fail(LM_ERR_NULL, "lm_forward_pcm16: d_pcm and d_out must be non-NULL");
+  return forward_impl(h, nullptr, d_pcm, channels, batch, clip_stride, n_samples, d_lengths, d_out, d_clip_max, d_scratch,
+                      scratch_bytes, stream);
 }
 
 int lm_host_register(void* p, size_t bytes) {
@@ -430,9 +481,16 @@ int lm_host_unregister(void* p) {
   return 0;
 }
 
-int lm_forward_host(lm_handle* h, const float* h_wave, int64_t batch, int64_t clip_stride, int64_t n_samples,
-                    const int32_t* h_lengths, float* h_out) {
+}  // extern "C"
+
+namespace {
+// h_wave: float32 samples (channels == 0) or int16 PCM frames of `channels` interleaved channels
+int forward_host_impl(lm_handle* h, const void* h_wave_v, int channels, int64_t batch, int64_t clip_stride, int64_t n_samples,
+                      const int32_t* h_lengths, float* h_out) {
+  const char* h_wave = static_cast<const char*>(h_wave_v);
+  const size_t elem = channels ? (size_t)2 * channels : 4;         // bytes per sample / frame
   if (!h) return fail(LM_ERR_NULL, "lm_forward_host: NULL handle");
+  if (channels != 0 && channels != 1 && channels != 2) return fail(LM_ERR_SHAPE, "channels=%d: 16-bit PCM input is mono or stereo", channels);
   if (batch == 0) return 0;
   if (!h_wave || !h_out) return fail(LM_ERR_NULL, "lm_forward_host: h_wave and h_out must be non-NULL");
   const lm_config& c = h->cfg;
@@ -441,12 +499,13 @@ int lm_forward_host(lm_handle* h, const float* h_wave, int64_t batch, int64_t cl
   const int64_t n_frames = frames_for(c, n_samples);
   if (n_frames < 1) return fail(LM_ERR_SHAPE, "n_samples=%lld gives no frame", (long long)n_samples);
   std::lock_guard<std::mutex> lock(h->host_mu);
-  int dev = -1;
-  CUDA_TRY(cudaGetDevice(&dev));
-  if (dev != c.device) CUDA_TRY(cudaSetDevice(c.device));
+  DeviceGuard guard(c.device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
 
   // chunking: ~64 MiB of waveform per chunk, at least 1 clip, at most the whole batch
-  const size_t clip_in = (size_t)n_samples * 4, clip_out = (size_t)c.n_mels * n_frames * 4;
+  // (a PCM row is padded to a multiple of 8 frames so that every staged clip starts 16-byte aligned)
+  const int64_t dev_stride = channels ? (n_samples + 7) / 8 * 8 : n_samples;
+  const size_t clip_in = (size_t)dev_stride * elem, clip_out = (size_t)c.n_mels * n_frames * 4;
   int64_t chunk = std::max<int64_t>(1, (int64_t)((64u << 20) / clip_in));
   chunk = std::min(chunk, batch);
   // copy width: clips shorter than n_samples on the host are copied at their stride
@@ -487,19 +546,21 @@ int lm_forward_host(lm_handle* h, const float* h_wave, int64_t batch, int64_t cl
       CUDA_TRY(cudaStreamWaitEvent(p.s_h2d, p.ev_comp[b], 0));
       CUDA_TRY(cudaStreamWaitEvent(p.s_comp, p.ev_d2h[b], 0));
     }
-    if (row == n_samples && clip_stride == n_samples) {
-      CUDA_TRY(cudaMemcpyAsync(p.d_wave[b], h_wave + c0 * clip_stride, (size_t)nb * clip_in, cudaMemcpyHostToDevice, p.s_h2d));
+    if (row == n_samples && clip_stride == n_samples && dev_stride == n_samples) {
+      CUDA_TRY(cudaMemcpyAsync(p.d_wave[b], h_wave + (size_t)c0 * clip_stride * elem, (size_t)nb * clip_in,
+                               cudaMemcpyHostToDevice, p.s_h2d));
     } else {
-      if (row < n_samples) CUDA_TRY(cudaMemsetAsync(p.d_wave[b], 0, (size_t)nb * clip_in, p.s_h2d));
-      CUDA_TRY(cudaMemcpy2DAsync(p.d_wave[b], clip_in, h_wave + c0 * clip_stride, (size_t)clip_stride * 4,
-                                 (size_t)row * 4, (size_t)nb, cudaMemcpyHostToDevice, p.s_h2d));
+      if (row < dev_stride) CUDA_TRY(cudaMemsetAsync(p.d_wave[b], 0, (size_t)nb * clip_in, p.s_h2d));
+      CUDA_TRY(cudaMemcpy2DAsync(p.d_wave[b], clip_in, h_wave + (size_t)c0 * clip_stride * elem, (size_t)clip_stride * elem,
+                                 (size_t)row * elem, (size_t)nb, cudaMemcpyHostToDevice, p.s_h2d));
     }
     if (h_lengths)
       CUDA_TRY(cudaMemcpyAsync(p.d_len[b], h_lengths + c0, (size_t)nb * 4, cudaMemcpyHostToDevice, p.s_h2d));
     CUDA_TRY(cudaEventRecord(p.ev_h2d[b], p.s_h2d));
     CUDA_TRY(cudaStreamWaitEvent(p.s_comp, p.ev_h2d[b], 0));
-    int rc = lm_forward(h, p.d_wave[b], nb, n_samples, n_samples, h_lengths ? p.d_len[b] : nullptr, p.d_out[b],
-                        nullptr, p.d_scratch[b], p.scratch_cap, p.s_comp);
+    int rc = forward_impl(h, channels ? nullptr : p.d_wave[b], channels ? reinterpret_cast<const int16_t*>(p.d_wave[b]) : nullptr,
+                          channels, nb, dev_stride, n_samples, h_lengths ? p.d_len[b] : nullptr, p.d_out[b], nullptr,
+                          p.d_scratch[b], p.scratch_cap, p.s_comp);
     if (rc != 0) return rc;
     CUDA_TRY(cudaEventRecord(p.ev_comp[b], p.s_comp));
     CUDA_TRY(cudaStreamWaitEvent(p.s_d2h, p.ev_comp[b], 0));
@@ -510,8 +571,21 @@ int lm_forward_host(lm_handle* h, const float* h_wave, int64_t batch, int64_t cl
   CUDA_TRY(cudaStreamSynchronize(p.s_d2h));
   CUDA_TRY(cudaStreamSynchronize(p.s_comp));
   CUDA_TRY(cudaStreamSynchronize(p.s_h2d));
-  if (dev != c.device && dev >= 0) cudaSetDevice(dev);
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int lm_forward_host(lm_handle* h, const float* h_wave, int64_t batch, int64_t clip_stride, int64_t n_samples,
+                    const int32_t* h_lengths, float* h_out) {
+  return forward_host_impl(h, h_wave, 0, batch, clip_stride, n_samples, h_lengths, h_out);
+}
+
+int lm_forward_host_pcm16(lm_handle* h, const int16_t* h_pcm, int32_t channels, int64_t batch, int64_t clip_stride,
+                          int64_t n_samples, const int32_t* h_lengths, float* h_out) {
+  if (channels != 1 && channels != 2) return fail(LM_ERR_SHAPE, "channels=%d: 16-bit PCM input is mono or stereo", channels);
+  return forward_host_impl(h, h_pcm, channels, batch, clip_stride, n_samples, h_lengths, h_out);
 }
 
 }  // extern "C"

@@ -36,7 +36,7 @@ template <> struct Split<400> { static constexpr int N1 = 20, N2 = 20; };
 template <> struct Split<1024> { static constexpr int N1 = 32, N2 = 32; };
 
 // WS_ = 1: warp-specialised CTA (logmel_ws_kernel.cuh): warps [0, NW_FFT) run the two DFT stages,
-// warps [NW_FFT, NWK) run the mel projection / log / stores and issue the TMA tile copies.
+// warps [NW_FFT, NWK) run the mel projection / log / stores.
 template <int NFFT, int HOP_, int PK_, int WS_ = 0>
 struct Geo {
   static constexpr int N = NFFT, HOP = HOP_, PK = PK_, WS = WS_;
@@ -137,6 +137,24 @@ LM_HD float load_sample(const float* __restrict__ clip, long s, int n_samples, i
   if (s >= n_samples) s = 2L * (n_samples - 1) - s;
   if (s < 0 || s >= valid) return 0.0f;
   return clip[s];
+}
+
+// The same for 16-bit PCM input (fused ingest): `pcm` holds interleaved frames of
+// `ch` channels (1 or 2), and the sample is what the reference's loaders make of them --
+// torchaudio.load's s / 32768 (/root/reference/AB/wavToWhisper.py:52, AB/memoToWav.py:19 writes s16 mono)
+// and the mono mix waveform.mean(dim=0) of /root/reference/.charles/spectrogram.py:147-148.  Sums of
+// two int16 and the scale by a power of two are exact in float32, so this equals the float path bit
+// for bit.
+LM_HD float pcm_to_float(int sum, int ch) { return (float)sum * (ch == 2 ? (1.0f / 65536.0f) : (1.0f / 32768.0f)); }
+LM_HD float load_sample_pcm(const short* __restrict__ pcm, int ch, long s, int n_samples, int valid) {
+  if (s < 0) s = -s;
+  if (s >= n_samples) s = 2L * (n_samples - 1) - s;
+  if (s < 0 || s >= valid) return 0.0f;
+  return ch == 2 ? pcm_to_float((int)pcm[2 * s] + (int)pcm[2 * s + 1], 2) : pcm_to_float((int)pcm[s], 1);
+}
+LM_HD float load_sample_any(const float* __restrict__ clip, const short* __restrict__ pcm, int ch, long s, int n_samples,
+                            int valid) {
+  return pcm ? load_sample_pcm(pcm, ch, s, n_samples, valid) : load_sample(clip, s, n_samples, valid);
 }
 
 template <class G> LM_HD int wave_index(int r) { return r + 4 * (r / G::HOP); }

@@ -16,8 +16,10 @@
 namespace lm {
 
 struct KArgs {
-  const float* wave;
-  long long clip_stride;
+  const float* wave;         // float32 clips, or NULL when pcm is set
+  const short* pcm;          // 16-bit PCM clips: interleaved frames of pcm_channels channels (fused ingest)
+  int pcm_channels;          // 1 or 2 (the kernel averages the channels)
+  long long clip_stride;     // samples (PCM: frames) between clip starts
   const int* lengths;
   float* out;
   float* clip_max;   // optional user-visible per-clip max
@@ -146,7 +148,8 @@ __device__ __forceinline__ int tile_plan(long long s0, int valid, bool tma_ok, i
 template <class G, int NW = G::NWK>
 __device__ __forceinline__ int load_tile(float* wave_s, const float* __restrict__ clip, long long s0, int n_samples,
                                          int valid, bool tma_ok, unsigned long long* bar, int warp, int lane,
-                                         int loader, int iss = -1, int n_iss = 0) {
+                                         int loader, int iss = -1, int n_iss = 0, const short* pcm = nullptr,
+                                         int pcm_ch = 0) {
   constexpr int FULL_ROWS = G::SPAN / G::HOP;
   constexpr int REM = G::SPAN - FULL_ROWS * G::HOP;
   constexpr int ROWS = FULL_ROWS + (REM > 0 ? 1 : 0);
@@ -208,7 +211,8 @@ __device__ __forceinline__ int load_tile(float* wave_s, const float* __restrict_
         if (lane == 0) bulk_g2s(wave_s + row * G::PITCH, clip + s0 + (long long)row * G::HOP, len * 4, bar);
       } else {
         for (int i = lane; i < len; i += 32)
-          wave_s[row * G::PITCH + i] = load_sample(clip, (long)(s0 + (long long)row * G::HOP + i), n_samples, valid);
+          wave_s[row * G::PITCH + i] =
+              load_sample_any(clip, pcm, pcm_ch, (long)(s0 + (long long)row * G::HOP + i), n_samples, valid);
       }
     }
   }
@@ -363,6 +367,7 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
   int par = 0;
   for (int clip = group_id; clip < a.batch; clip += a.n_groups, par ^= 1) {
     const float* cptr = a.wave + (long long)clip * a.clip_stride;
+    const short* pptr = a.pcm ? a.pcm + (long long)clip * a.clip_stride * a.pcm_channels : nullptr;
     int valid = a.n_samples;
     if (a.lengths) valid = min(max(a.lengths[clip], 0), a.n_samples);
     float* oc = a.out + (long long)clip * a.n_mels * a.n_frames;
@@ -373,7 +378,8 @@ logmel_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
     // CTA-uniform: start filling wave_s with the tile that begins at sample s; returns whether
     // some rows were written by threads (then a CTA barrier must precede their use)
     auto fetch = [&](long long s) -> bool {
-      const int how = load_tile<G>(wave_s, cptr, s, a.n_samples, valid, a.tma_ok != 0, &s_mbar, warp, lane, loader);
+      const int how = load_tile<G>(wave_s, cptr, s, a.n_samples, valid, a.tma_ok != 0, &s_mbar, warp, lane, loader, -1, 0,
+                                   pptr, a.pcm_channels);
       staged_tma = (how & 1) != 0;
       return (how & 2) != 0;
     };

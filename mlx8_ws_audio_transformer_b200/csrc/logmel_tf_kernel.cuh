@@ -340,6 +340,7 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
   const int gn = gridDim.x * G::PAIRS;
   for (int clip = gp; clip < a.batch; clip += gn) {
     const float* cptr = a.wave + (long long)clip * a.clip_stride;
+    const short* pptr = a.pcm ? a.pcm + (long long)clip * a.clip_stride * a.pcm_channels : nullptr;
     int valid = a.n_samples;
     if (a.lengths) valid = min(max(a.lengths[clip], 0), a.n_samples);
     float* oc = a.out + (long long)clip * NM * n_frames;
@@ -371,8 +372,37 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
     auto fetch_begin = [&](int t) {
       const long long s0 = tile_s0(t);
       fsrc = nullptr;
-      if (s0 >= 0 && s0 + G::SPAN <= valid) {
+      const bool interior = s0 >= 0 && s0 + G::SPAN <= valid;
+      if (interior && !pptr) {
         fsrc = reinterpret_cast<const char*>(cptr + s0) + 16 * lane + role * (4 * 4 * G::HOP * 4);
+        return;
+      }
+      if (interior && a.tma_ok) {
+        // 16-bit PCM (fused ingest): 16-byte chunks = 8 mono samples / 4 stereo frames, converted
+        // (and down-mixed) on their way into the float tile; this warp's half of the tile
+        const int spc = a.pcm_channels == 2 ? 4 : 8;               // samples per chunk
+        const int half = G::SPAN / spc / 2;
+        const uint4* src = reinterpret_cast<const uint4*>(pptr + s0 * a.pcm_channels);
+#pragma unroll 4
+        for (int c = role * half + lane; c < (role + 1) * half; c += 32) {
+          const uint4 v = __ldg(src + c);
+          const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int lo = (int)(short)(wds[j] & 0xffffu), hi = (int)(short)(wds[j] >> 16);
+            if (spc == 4) {
+              f[j] = pcm_to_float(lo + hi, 2);
+            } else {
+              f[2 * j] = pcm_to_float(lo, 1);
+              f[2 * j + 1] = pcm_to_float(hi, 1);
+            }
+          }
+          const int n0 = c * spc;                                   // first sample of the chunk (never straddles a hop row)
+          float* d = tile + n0 + 4 * (n0 / G::HOP);
+          *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
+          if (spc == 8) *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
         return;
       }
 #pragma unroll 1
@@ -380,10 +410,11 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
         const long long sr = s0 + (long long)r * G::HOP;
         const int len = r == G::ROWS - 1 ? G::SPAN - (G::ROWS - 1) * G::HOP : G::HOP;
         float* drow = tile + r * G::PITCH;
-        if (sr >= 0 && sr + len <= valid) {
+        if (sr >= 0 && sr + len <= valid && !pptr) {
           for (int c = lane; c < len / 4; c += 32) cp_async16(drow + 4 * c, cptr + sr + 4 * c);
         } else {
-          for (int i = lane; i < len; i += 32) drow[i] = load_sample(cptr, (long)(sr + i), a.n_samples, valid);
+          for (int i = lane; i < len; i += 32)
+            drow[i] = load_sample_any(cptr, pptr, a.pcm_channels, (long)(sr + i), a.n_samples, valid);
         }
       }
     };

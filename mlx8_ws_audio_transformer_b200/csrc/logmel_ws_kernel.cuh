@@ -9,8 +9,9 @@
 //   warps 0..7   (two per SM sub-partition)  stage 1 and stage 2 -- the FP32-pipe-bound work;
 //                the codelets saturate the pipe from a single warp (profiles/r01_codelet_rate_*)
 //   warps 8..11  (one per sub-partition)     mel projection, log, global stores, running max /
-//                tile min, AND the TMA tile copies for the next tile -- the latency-bound work,
-//                software pipelined (mel_task_pipe), issued into the slots the FFT warps leave
+//                tile min -- the latency-bound work, software pipelined (mel_task_pipe), issued
+//                into the slots the FFT warps leave.  (The TMA tile copies of the next tile are
+//                issued by the FFT warps that own a single stage-2 row, see tab.tma_iss.)
 //
 // The two roles are decoupled by a full tile period.  Stage 2 writes the power spectrum IN PLACE
 // over its own row of the real plane of Y (stage2_task_inplace), and that plane is double
@@ -113,6 +114,7 @@ logmel_ws_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
     unsigned parity = 0;
     for (int clip = group_id; clip < a.batch; clip += a.n_groups) {
       const float* cptr = a.wave + (long long)clip * a.clip_stride;
+      const short* pptr = a.pcm ? a.pcm + (long long)clip * a.clip_stride * a.pcm_channels : nullptr;
       int valid = a.n_samples;
       if (a.lengths) valid = min(max(a.lengths[clip], 0), a.n_samples);
       auto next_loud = [&](int t) {
@@ -122,7 +124,7 @@ logmel_ws_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
       int how = 0;
       auto fetch = [&](long long s) {            // start filling wave_s (dead at this point)
         how = load_tile<G, G::NW_FFT>(wave_s, cptr, s, a.n_samples, valid, a.tma_ok != 0, &s_mbar, warp, lane, -1,
-                                          tab.tma_iss[warp], tab.n_tma_iss);
+                                          tab.tma_iss[warp], tab.n_tma_iss, pptr, a.pcm_channels);
       };
       auto do_s1 = [&](int i) __attribute__((always_inline)) {   // tile i: wave -> Yre[i & 1], Yim
         if (how & 2) nbar_sync(BAR_WAVE, NTF);                   // rows written by threads

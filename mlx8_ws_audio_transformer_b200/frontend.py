@@ -43,7 +43,6 @@ class LogMelFrontend:
         h = ctypes.c_void_p()
         N.check(self._lib.lm_create(ctypes.byref(h), ctypes.byref(cfg)), "lm_create")
         self._h = h
-        self._scratch = None
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None
@@ -71,12 +70,24 @@ class LogMelFrontend:
         return self._lib.lm_kernel_name(self._h, int(batch), int(n_samples)).decode()
 
     def _scratch_for(self, batch: int):
+        """Per-CALL scratch from torch's caching allocator: the block belongs to the current stream, so
+        two forward() calls of one (shared, cached) frontend on different streams never see each
+        other's clip counters, and a block is only reused after the launch that used it."""
         import torch
 
         need = int(self._lib.lm_scratch_bytes(self._h, batch))
-        if self._scratch is None or self._scratch.numel() < need:
-            self._scratch = torch.empty(need, dtype=torch.uint8, device=f"cuda:{self.device_index}")
-        return self._scratch
+        return torch.empty(max(need, 16), dtype=torch.uint8, device=f"cuda:{self.device_index}")
+
+    def _check_out(self, t, shape, name: str, device_type: str):
+        import torch
+
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if t.dtype != torch.float32 or tuple(t.shape) != tuple(shape) or not t.is_contiguous() or t.device.type != device_type:
+            raise ValueError(f"{name} must be a contiguous float32 {device_type} tensor of shape {tuple(shape)}, "
+                             f"got {t.dtype} {tuple(t.shape)} on {t.device} (contiguous={t.is_contiguous()})")
+        if device_type == "cuda" and t.device.index != self.device_index:
+            raise ValueError(f"{name} is on cuda:{t.device.index}, handle on cuda:{self.device_index}")
 
     def forward(self, wave, lengths=None, n_samples: int | None = None, out=None, clip_max=None):
         """Device-resident path: ``wave`` float32 CUDA ``[B, T]`` -> float32 CUDA ``[B, n_mels, frames]``.
@@ -89,13 +100,25 @@ class LogMelFrontend:
 
         if not (isinstance(wave, torch.Tensor) and wave.is_cuda):
             raise TypeError("forward() takes a CUDA tensor; use forward_host() for host buffers")
-        if wave.dtype != torch.float32:
+        channels = 0
+        if wave.dtype == torch.int16:
+            # 16-bit PCM as a WAV file holds it: [B, T] mono or [B, T, C] interleaved frames (C = 1, 2);
+            # converted (x / 32768) and down-mixed (mean over channels) inside the kernel's tile loader
+            if wave.dim() == 1:
+                wave = wave[None, :]
+            channels = 1 if wave.dim() == 2 else int(wave.shape[2]) if wave.dim() == 3 else -1
+            if channels not in (1, 2):
+                raise ValueError("int16 PCM must be [B, T] (mono) or [B, T, C] with C = 1 or 2 interleaved channels")
+            wave = wave.contiguous()
+            pcm = wave
+            wave = wave.reshape(wave.shape[0], -1)[:, ::channels]      # [B, T] view: shape bookkeeping only
+        elif wave.dtype != torch.float32:
             wave = wave.float()
         if wave.dim() == 1:
             wave = wave[None, :]
         if wave.dim() != 2:
             raise ValueError("wave must be [B, T]")
-        if wave.stride(1) != 1:
+        if not channels and wave.stride(1) != 1:
             wave = wave.contiguous()
         if wave.device.index != self.device_index:
             raise ValueError(f"wave is on cuda:{wave.device.index}, handle on cuda:{self.device_index}")
@@ -104,19 +127,33 @@ class LogMelFrontend:
         if lengths is None and L > T:
             lengths = torch.full((B,), T, dtype=torch.int32, device=wave.device)
         if lengths is not None:
-            lengths = lengths.to(device=wave.device, dtype=torch.int32).contiguous()
+            # never read past a row: the kernel clamps to n_samples, the row may be shorter than that
+            lengths = lengths.to(device=wave.device, dtype=torch.int32).clamp(0, T).contiguous()
+            if lengths.shape != (B,):
+                raise ValueError(f"lengths must have shape ({B},), got {tuple(lengths.shape)}")
         frames = self.num_frames(L)
         if out is None:
             out = torch.empty((B, self.n_mels, max(frames, 0)), dtype=torch.float32, device=wave.device)
+        else:
+            self._check_out(out, (B, self.n_mels, max(frames, 0)), "out", "cuda")
+        if clip_max is not None:
+            self._check_out(clip_max, (B,), "clip_max", "cuda")
         if B == 0:
             return out
         scratch = self._scratch_for(B)
         stream = torch.cuda.current_stream(wave.device).cuda_stream
-        rc = self._lib.lm_forward(
-            self._h, wave.data_ptr(), B, wave.stride(0) if B > 1 else max(T, 1), L,
-            None if lengths is None else lengths.data_ptr(), out.data_ptr(),
-            None if clip_max is None else clip_max.data_ptr(), scratch.data_ptr(), scratch.numel(),
-            ctypes.c_void_p(stream))
+        if channels:
+            rc = self._lib.lm_forward_pcm16(
+                self._h, pcm.data_ptr(), channels, B, max(T, 1), L,
+                None if lengths is None else lengths.data_ptr(), out.data_ptr(),
+                None if clip_max is None else clip_max.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                ctypes.c_void_p(stream))
+        else:
+            rc = self._lib.lm_forward(
+                self._h, wave.data_ptr(), B, wave.stride(0) if B > 1 else max(T, 1), L,
+                None if lengths is None else lengths.data_ptr(), out.data_ptr(),
+                None if clip_max is None else clip_max.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                ctypes.c_void_p(stream))
         N.check(rc, "lm_forward")
         return out
 
@@ -130,28 +167,45 @@ class LogMelFrontend:
 
         is_torch = isinstance(wave, torch.Tensor)
         w = wave if is_torch else torch.from_numpy(np.ascontiguousarray(wave, dtype=np.float32))
+        if not is_torch and np.asarray(wave).dtype == np.int16:
+            w = torch.from_numpy(np.ascontiguousarray(wave))
         if w.is_cuda:
             raise TypeError("forward_host() takes host buffers")
-        if w.dtype != torch.float32:
+        channels = 0
+        if w.dtype == torch.int16:                     # 16-bit PCM: [B, T] or [B, T, C] (see forward())
+            if w.dim() == 1:
+                w = w[None, :]
+            channels = 1 if w.dim() == 2 else int(w.shape[2]) if w.dim() == 3 else -1
+            if channels not in (1, 2):
+                raise ValueError("int16 PCM must be [B, T] (mono) or [B, T, C] with C = 1 or 2 interleaved channels")
+        elif w.dtype != torch.float32:
             w = w.float()
         if w.dim() == 1:
             w = w[None, :]
-        if w.dim() != 2:
+        if not channels and w.dim() != 2:
             raise ValueError("wave must be [B, T]")
         w = w.contiguous()
-        B, T = w.shape
+        B, T = w.shape[0], w.shape[1]
         L = T if n_samples is None else int(n_samples)
         len_t = None
         if lengths is not None:
-            len_t = torch.as_tensor(lengths, dtype=torch.int32).contiguous()
+            len_t = torch.as_tensor(lengths, dtype=torch.int32).clamp(0, T).contiguous()
+            if len_t.shape != (B,):
+                raise ValueError(f"lengths must have shape ({B},), got {tuple(len_t.shape)}")
         elif L > T:
             len_t = torch.full((B,), T, dtype=torch.int32)
         frames = self.num_frames(L)
         if out is None:
             out = torch.empty((B, self.n_mels, max(frames, 0)), dtype=torch.float32)
-        elif not isinstance(out, torch.Tensor):
-            out = torch.from_numpy(out)
-        if B:
+        else:
+            if not isinstance(out, torch.Tensor):
+                out = torch.from_numpy(out)
+            self._check_out(out, (B, self.n_mels, max(frames, 0)), "out", "cpu")
+        if B and channels:
+            rc = self._lib.lm_forward_host_pcm16(self._h, w.data_ptr(), channels, B, T, L,
+                                                 None if len_t is None else len_t.data_ptr(), out.data_ptr())
+            N.check(rc, "lm_forward_host_pcm16")
+        elif B:
             rc = self._lib.lm_forward_host(self._h, w.data_ptr(), B, T, L,
                                            None if len_t is None else len_t.data_ptr(), out.data_ptr())
             N.check(rc, "lm_forward_host")

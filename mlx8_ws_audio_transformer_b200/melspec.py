@@ -52,6 +52,10 @@ class MelSpectrogram(torch.nn.Module):
             raise NotImplementedError(
                 "MelSpectrogram(b200): only power=2.0, normalized=False, center=True, pad_mode='reflect', "
                 "pad=0, win_length=n_fft, onesided spectra are implemented")
+        if (n_fft, self.hop_length) not in ((1024, 512), (1024, 128), (400, 160)):
+            raise NotImplementedError(
+                f"MelSpectrogram(b200): no kernel for n_fft={n_fft}, hop_length={self.hop_length}; "
+                "implemented: (1024, 512), (1024, 128), (400, 160)")
         window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
         self.register_buffer("window", window.to(torch.float32), persistent=False)
         fb = torchaudio_mel_filter_bank(n_fft // 2 + 1, self.f_min, self.f_max, n_mels, sample_rate, norm, mel_scale)

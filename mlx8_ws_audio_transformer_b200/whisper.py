@@ -13,6 +13,8 @@ Beyond the HF contract, a CUDA tensor in gives a CUDA tensor out with no host ro
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 from transformers import WhisperFeatureExtractor
 from transformers.feature_extraction_utils import BatchFeature
@@ -24,6 +26,10 @@ from .frontend import LogMelFrontend
 logger = hf_logging.get_logger(__name__)
 
 _FRONTENDS: dict = {}
+# float32 image of an extractor's filter bank and its hash, computed once per instance (not per call:
+# the music2midi loop of /root/reference/.charles/music2midi/model.py:96-110 calls the extractor per
+# clip).  Kept outside the instance so that the extractor stays a plain JSON-serialisable HF object.
+_BANKS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
 class LogMelWhisperFeatureExtractor(WhisperFeatureExtractor):
@@ -52,8 +58,13 @@ class LogMelWhisperFeatureExtractor(WhisperFeatureExtractor):
             idx = torch.cuda.current_device() if torch.cuda.is_available() else 0
         # handles are cached per (geometry, bank, device) outside the instance, so the extractor
         # itself stays a plain, copyable, JSON-serialisable HF object
-        fb32 = np.ascontiguousarray(self.mel_filters, dtype=np.float32)
-        key = (self.n_fft, self.hop_length, fb32.shape, hash(fb32.tobytes()), idx, self.lm_variant)
+        bank = _BANKS.get(self)
+        if bank is None or bank[0] is not self.mel_filters:
+            fb32 = np.ascontiguousarray(self.mel_filters, dtype=np.float32)
+            bank = (self.mel_filters, fb32, hash(fb32.tobytes()))
+            _BANKS[self] = bank
+        fb32 = bank[1]
+        key = (self.n_fft, self.hop_length, fb32.shape, bank[2], idx, self.lm_variant)
         fe = _FRONTENDS.get(key)
         if fe is None:
             fe = LogMelFrontend(self.n_fft, self.hop_length, fb32, N.LOG10_CLAMP_WHISPER_NORM,
@@ -67,8 +78,9 @@ class LogMelWhisperFeatureExtractor(WhisperFeatureExtractor):
         squeeze = waveform.ndim == 1
         if squeeze:
             waveform = waveform[None, :]
-        if self.dither != 0.0:
-            waveform = waveform + self.dither * np.random.randn(*waveform.shape).astype(np.float32)
+        dither = getattr(self, "dither", 0.0)
+        if dither != 0.0:
+            waveform = waveform + dither * np.random.randn(*waveform.shape).astype(np.float32)
         out = self._frontend(device).forward_host(waveform)
         return out[0] if squeeze else out
 
@@ -92,11 +104,16 @@ class LogMelWhisperFeatureExtractor(WhisperFeatureExtractor):
                 f"It is strongly recommended to pass the `sampling_rate` argument to `{self.__class__.__name__}()`. "
                 "Failing to do so can result in silent errors that might be hard to debug.")
 
+        # the kernel's own padding is zero padding, so the fast path needs padding_value == 0 (the default)
         fast = (padding == "max_length" and truncation and pad_to_multiple_of is None and not do_normalize
-                and self.dither == 0.0)
+                and getattr(self, "dither", 0.0) == 0.0 and self.padding_value == 0.0)
+        cuda_list = (isinstance(raw_speech, (list, tuple)) and len(raw_speech) > 0
+                     and all(isinstance(c, torch.Tensor) and c.is_cuda for c in raw_speech))
         if not fast:
             if isinstance(raw_speech, torch.Tensor):
                 raw_speech = raw_speech.detach().cpu().numpy()
+            elif cuda_list:
+                raw_speech = [c.detach().cpu().numpy() for c in raw_speech]
             # HF's own host glue (pad / normalise / mask), with the kernel behind the extractor hooks
             return super().__call__(raw_speech, truncation=truncation, pad_to_multiple_of=pad_to_multiple_of,
                                     return_tensors=return_tensors, return_attention_mask=return_attention_mask,
@@ -106,13 +123,28 @@ class LogMelWhisperFeatureExtractor(WhisperFeatureExtractor):
         n_samples = max_length if max_length else self.n_samples
         want_mask = return_attention_mask if return_attention_mask is not None else self.return_attention_mask
 
-        # ---- device-resident path: CUDA tensor in, CUDA tensor out -------------------------
-        if isinstance(raw_speech, torch.Tensor) and raw_speech.is_cuda:
-            if raw_speech.dim() > 2:
-                raise ValueError(f"Only mono-channel audio is supported for input to {self}")
-            w = raw_speech if raw_speech.dim() == 2 else raw_speech[None, :]
-            lengths = torch.full((w.shape[0],), min(w.shape[1], n_samples), dtype=torch.int32)
-            feats = self._frontend(w.device).forward(w, n_samples=n_samples)
+        # ---- device-resident path: CUDA tensor(s) in, CUDA tensor out -----------------------
+        # A [B, T] tensor, a 1-D tensor, or a LIST of ragged 1-D CUDA tensors -- the batch
+        # WhisperAudioEncoder.forward (/root/reference/.charles/music2midi/model.py:94-123) walks
+        # clip by clip through the processor: here it is ONE launch with per-clip lengths.
+        if cuda_list or (isinstance(raw_speech, torch.Tensor) and raw_speech.is_cuda):
+            if cuda_list:
+                if any(c.dim() != 1 for c in raw_speech):
+                    raise ValueError(f"Only mono-channel audio is supported for input to {self}")
+                lens = [min(int(c.shape[0]), n_samples) for c in raw_speech]
+                width = max(max(lens), 4)
+                width += (-width) % 4                      # 16-byte aligned rows
+                w = torch.zeros((len(raw_speech), width), dtype=torch.float32, device=raw_speech[0].device)
+                for i, c in enumerate(raw_speech):
+                    w[i, :lens[i]] = c[:lens[i]]
+                lengths = torch.tensor(lens, dtype=torch.int32)
+                feats = self._frontend(w.device).forward(w, lengths=lengths.to(w.device), n_samples=n_samples)
+            else:
+                if raw_speech.dim() > 2:
+                    raise ValueError(f"Only mono-channel audio is supported for input to {self}")
+                w = raw_speech if raw_speech.dim() == 2 else raw_speech[None, :]
+                lengths = torch.full((w.shape[0],), min(w.shape[1], n_samples), dtype=torch.int32)
+                feats = self._frontend(w.device).forward(w, n_samples=n_samples)
             data = {"input_features": feats}
             if want_mask:
                 data["attention_mask"] = torch.from_numpy(self._frame_mask(lengths.numpy(), n_samples)).to(w.device)

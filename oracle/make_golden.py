@@ -102,8 +102,99 @@ def main():
         save[f"logmel_{hop}_{nm}"] = torch.log(mel + 1e-6).numpy()
         save[f"fb_{hop}_{nm}"] = ms.mel_scale.fb.numpy()
     np.savez_compressed(os.path.join(OUT, "torchaudio_4s.npz"), **save)
+    make_refwav(versions)
+    make_configs(versions)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+REFWAV_FRAMES = 32000      # first 2 s of every reference WAV (keeps the fixture at a few MB)
+REFWAV_STRIDE = 3
+
+
+def make_refwav(versions: str):
+    """The 18 real-audio fixtures the reference ships (/root/reference/.charles/samples/**/*.wav: 16 kHz,
+    stereo, s16), through the reference's own two calls:
+      * every channel as a clip and the mono mix through WhisperFeatureExtractor (the [2, N] array of
+        /root/reference/AB/wavToWhisper.py:52-55 is a batch of two clips, feature_extraction_whisper.py:274-279);
+      * the mono mix (waveform.mean(dim=0), /root/reference/.charles/spectrogram.py:147-148), zero padded to
+        4 s (:152-157), through torchaudio MelSpectrogram + torch.log(mel + 1e-6) (:161-162).
+    The decoded PCM is stored as int16 so that the fused int16 / stereo ingest is tested on it too."""
+    import glob
+    import wave
+
+    import torch
+    import torchaudio
+    from transformers import WhisperFeatureExtractor
+
+    files = sorted(glob.glob("/root/reference/.charles/samples/**/*.wav", recursive=True))
+    if not files:
+        print("no /root/reference: refwav.npz left as it is")
+        return
+    pcm = np.zeros((len(files), REFWAV_FRAMES, 2), np.int16)
+    names = []
+    for i, f in enumerate(files):
+        with wave.open(f) as w:
+            assert w.getnchannels() == 2 and w.getsampwidth() == 2 and w.getframerate() == 16000
+            raw = np.frombuffer(w.readframes(REFWAV_FRAMES), dtype="<i2").reshape(-1, 2)
+        pcm[i, :len(raw)] = raw
+        names.append(os.path.relpath(f, "/root/reference/.charles/samples"))
+    chan = (pcm.astype(np.float32) / 32768.0)                              # torchaudio.load's normalisation
+    mono = chan.mean(axis=2).astype(np.float32)                            # == (l + r) / 65536 exactly
+    per_channel = np.ascontiguousarray(chan.transpose(0, 2, 1)).reshape(-1, REFWAV_FRAMES)   # [36, N]
+    save = {"versions": np.array(versions), "names": np.array(names), "pcm": pcm, "stride": np.array(REFWAV_STRIDE)}
+    fe80, fe128 = WhisperFeatureExtractor(feature_size=80), WhisperFeatureExtractor(feature_size=128)
+    kw = dict(sampling_rate=16000, max_length=REFWAV_FRAMES, return_tensors="np")
+    save["feat80_channels"] = fe80(list(per_channel), **kw)["input_features"][:, :, ::REFWAV_STRIDE].astype(np.float32)
+    save["feat80_mono"] = fe80(list(mono), **kw)["input_features"][:, :, ::REFWAV_STRIDE].astype(np.float32)
+    save["feat128_mono"] = fe128(list(mono), **kw)["input_features"][:, :, ::REFWAV_STRIDE].astype(np.float32)
+    padded = np.zeros((len(files), 64000), np.float32)
+    padded[:, :REFWAV_FRAMES] = mono
+    ms = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=1024, hop_length=512, n_mels=128, f_min=0, f_max=8000, power=2.0)
+    save["ta_logmel_512_128"] = torch.log(ms(torch.from_numpy(padded)) + 1e-6).numpy()[:, :, ::REFWAV_STRIDE]
+    np.savez_compressed(os.path.join(OUT, "refwav.npz"), **save)
+
+
+def make_configs(versions: str):
+    """BASELINE configs 1 and 4 at their exact sizes, plus the __call__ branches the drop-in forwards to HF."""
+    from transformers import WhisperFeatureExtractor
+
+    fe = WhisperFeatureExtractor(feature_size=80)
+    save = {"versions": np.array(versions)}
+    # config 1: default_rng(0), B = 32, 80 mels, 30 s (SURVEY.md 8d)
+    x = synth.gaussian_clips(32, seed=0)
+    out = fe(list(x), sampling_rate=16000, return_tensors="np")["input_features"]
+    save["cfg1_stride"] = np.array(97)
+    save["cfg1_feat"] = np.ascontiguousarray(out[:, :, ::97]).astype(np.float32)
+    save["cfg1_max"] = out.reshape(32, -1).max(axis=1)
+    save["cfg1_mean"] = out.reshape(32, -1).mean(axis=1, dtype=np.float64)
+    # config 4: 1000 piano clips (one per row of /root/reference/AB/mididataset.csv), mostly zero padding
+    w, n = synth.midi_piano_clips(1000, seed=0)
+    mx, mean, keep = [], [], {}
+    for s0 in range(0, 1000, 50):
+        o = fe(list(w[s0:s0 + 50]), sampling_rate=16000, return_tensors="np")["input_features"]
+        mx.append(o.reshape(50, -1).max(axis=1))
+        mean.append(o.reshape(50, -1).mean(axis=1, dtype=np.float64))
+        for i in range(s0, s0 + 50):
+            if i % 125 == 0:
+                keep[i] = np.ascontiguousarray(o[i - s0][:, ::29]).astype(np.float32)
+    save["cfg4_lengths"] = n
+    save["cfg4_max"] = np.concatenate(mx)
+    save["cfg4_mean"] = np.concatenate(mean)
+    save["cfg4_keep_idx"] = np.array(sorted(keep))
+    save["cfg4_keep_feat"] = np.stack([keep[i] for i in sorted(keep)])
+    save["cfg4_stride"] = np.array(29)
+    # the other __call__ branches: attention mask (feature_extraction_whisper.py:328-337) and
+    # do_normalize (:306-312) on ragged one-second-ish clips
+    ragged = [synth.gaussian_clips(1, L, seed=50 + i)[0] * (1 + i) for i, L in enumerate((16000, 9000, 399, 12345))]
+    for i, c in enumerate(ragged):
+        save[f"ragged_in{i}"] = c
+    o = fe(ragged, sampling_rate=16000, max_length=16000, return_attention_mask=True, return_tensors="np")
+    save["ragged_mask"] = o["attention_mask"].astype(np.int32)
+    save["ragged_feat"] = o["input_features"].astype(np.float32)
+    o = fe(ragged, sampling_rate=16000, max_length=16000, do_normalize=True, return_attention_mask=True, return_tensors="np")
+    save["ragged_feat_normalized"] = o["input_features"].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "whisper_cfg.npz"), **save)
 
 
 if __name__ == "__main__":

@@ -63,7 +63,7 @@ def emul():
     """Host emulation of the kernel (tests/emul/host_emul.cpp), built with g++ on first use."""
     src = os.path.join(ROOT, "tests", "emul", "host_emul.cpp")
     so = os.path.join(ROOT, "tests", "emul", "libhost_emul.so")
-    deps = [src] + [os.path.join(ROOT, "mlx8-ws-audio-transformer_b200", "csrc", f)
+    deps = [src] + [os.path.join(ROOT, "mlx8_ws_audio_transformer_b200", "csrc", f)
                     for f in ("codelets_gen.cuh", "vec_ops.cuh", "logmel_core.cuh", "logmel_tables.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", so], check=True)
@@ -87,3 +87,13 @@ def emul():
         return out
 
     return run
+
+
+@pytest.fixture(scope="session")
+def golden_refwav():
+    return np.load(os.path.join(GOLDEN, "refwav.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_cfg():
+    return np.load(os.path.join(GOLDEN, "whisper_cfg.npz"))

@@ -11,7 +11,7 @@
 #include <cstdio>
 #include <vector>
 
-#include "../../mlx8-ws-audio-transformer_b200/csrc/logmel_tables.h"
+#include "../../mlx8_ws_audio_transformer_b200/csrc/logmel_tables.h"
 
 namespace {
 

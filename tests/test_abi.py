@@ -14,7 +14,7 @@ from mlx8_ws_audio_transformer_b200 import shard_bounds, shard_sizes
 def _header_symbols():
     text = open(os.path.join(ROOT, "include", "logmel.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(lm_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(lm_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -59,7 +59,7 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "mlx8-ws-audio-transformer_b200")
+    pkg = os.path.join(ROOT, "mlx8_ws_audio_transformer_b200")
     for root, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
@@ -110,3 +110,23 @@ def test_filter_banks_equal_the_libraries(golden_whisper_short, golden_torchaudi
     torchaudio = pytest.importorskip("torchaudio")
     ref = torchaudio.functional.melscale_fbanks(513, 0.0, 8000.0, 40, 16000, norm="slaney", mel_scale="slaney")
     assert np.array_equal(torchaudio_mel_filter_bank(513, 0.0, 8000.0, 40, 16000, "slaney", "slaney").numpy(), ref.numpy())
+
+
+def test_generated_mel_code_is_current_and_bakes_the_hf_bank():
+    """csrc/tf_mel_gen.cuh holds the Whisper banks' weights as literals: it must be what tools/gen_tf_mel.py
+    emits today, and the literals must be the float32 image of WhisperFeatureExtractor.mel_filters."""
+    import re
+    import subprocess
+    import sys
+
+    gen = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_tf_mel.py")], capture_output=True, text=True, check=True).stdout
+    with open(os.path.join(ROOT, "mlx8_ws_audio_transformer_b200", "csrc", "tf_mel_gen.cuh")) as f:
+        assert f.read() == gen
+    from transformers import WhisperFeatureExtractor
+    for nm in (80, 128):
+        blk = gen[gen.index(f"struct TfMelPattern<{nm}>"):]
+        arr = lambda name: [int(v.rstrip("u"), 0) for v in re.search(name + r"\[NNZ\] = \{([^}]*)\}", blk).group(1).split(",")]
+        bins, mels, bits = arr("bin"), arr("mel"), arr("bits")
+        fb = WhisperFeatureExtractor(feature_size=nm).mel_filters.astype(np.float32)
+        assert len(bits) == int((fb != 0).sum())
+        assert np.array_equal(fb[bins, mels].view(np.uint32), np.array(bits, np.uint32))

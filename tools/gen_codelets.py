@@ -10,7 +10,7 @@ is ``float`` on the host / scalar device path and the packed ``f32x2`` type on t
 
 Nothing here is copied from FFTW's genfft; it is the same idea at toy size.
 
-    python tools/gen_codelets.py > mlx8-ws-audio-transformer_b200/csrc/codelets_gen.cuh
+    python tools/gen_codelets.py > mlx8_ws_audio_transformer_b200/csrc/codelets_gen.cuh
     python tools/gen_codelets.py --selftest
 """
 from __future__ import annotations

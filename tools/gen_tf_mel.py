@@ -11,7 +11,7 @@ weights are immediate operands of the FFMAs (loading 394 weights through uniform
 ~450 extra instructions per 32 frames, ptxas runs out of uniform registers).  lm_create compares
 lm_config.fbank with the baked table bit for bit; any other bank takes the table-driven kernels.
 
-    python tools/gen_tf_mel.py > mlx8-ws-audio-transformer_b200/csrc/tf_mel_gen.cuh
+    python tools/gen_tf_mel.py > mlx8_ws_audio_transformer_b200/csrc/tf_mel_gen.cuh
 """
 from __future__ import annotations
 
@@ -23,7 +23,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 spec = importlib.util.spec_from_file_location(
-    "lm_filters", os.path.join(ROOT, "mlx8-ws-audio-transformer_b200", "filters.py"))
+    "lm_filters", os.path.join(ROOT, "mlx8_ws_audio_transformer_b200", "filters.py"))
 filters = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(filters)
 

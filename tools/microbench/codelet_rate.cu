@@ -3,7 +3,7 @@
 // this isolates the FP32 pipe + scheduling from shared memory.
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "../../mlx8-ws-audio-transformer_b200/csrc/codelets_gen.cuh"
+#include "../../mlx8_ws_audio_transformer_b200/csrc/codelets_gen.cuh"
 using namespace lm;
 
 template <typename T> __device__ T mk(float a, float b);

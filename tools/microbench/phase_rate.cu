@@ -3,8 +3,8 @@
 #include <cstdio>
 #include <vector>
 #include <cuda_runtime.h>
-#include "../../mlx8-ws-audio-transformer_b200/csrc/logmel_tables.h"
-#include "../../mlx8-ws-audio-transformer_b200/csrc/logmel_kernel.cuh"
+#include "../../mlx8_ws_audio_transformer_b200/csrc/logmel_tables.h"
+#include "../../mlx8_ws_audio_transformer_b200/csrc/logmel_kernel.cuh"
 using namespace lm;
 
 template <class G>
