@@ -201,8 +201,8 @@ bool tf_fill(lm::TfTables& t, const float* window, const float* fbank) {
   for (int cp = 0; cp < 10; ++cp) {
     for (int a = 0; a < 20; ++a) {
       const float w0 = window[20 * a + 2 * cp], w1 = window[20 * a + 2 * cp + 1];
-      t.w[cp][a] = lm::tf_pack2(w0, w1);
-      t.nw[cp][a] = lm::tf_pack2(-w0, -w1);
+      t.cp[cp].w[a] = lm::tf_pack2(w0, w1);
+      t.cp[cp].nw[a] = lm::tf_pack2(-w0, -w1);
     }
     for (int k = 1; k <= 10; ++k) {
       float c[2], s[2];
@@ -211,10 +211,10 @@ bool tf_fill(lm::TfTables& t, const float* window, const float* fbank) {
         c[h] = (float)std::cos(ang);
         s[h] = (float)std::sin(ang);
       }
-      t.twr[cp][k - 1] = lm::tf_pack2(c[0], c[1]);
-      t.ntwr[cp][k - 1] = lm::tf_pack2(-c[0], -c[1]);
-      t.twi[cp][k - 1] = lm::tf_pack2(s[0], s[1]);
-      t.ntwi[cp][k - 1] = lm::tf_pack2(-s[0], -s[1]);
+      t.cp[cp].twr[k - 1] = lm::tf_pack2(c[0], c[1]);
+      t.cp[cp].ntwr[k - 1] = lm::tf_pack2(-c[0], -c[1]);
+      t.cp[cp].twi[k - 1] = lm::tf_pack2(s[0], s[1]);
+      t.cp[cp].ntwi[k - 1] = lm::tf_pack2(-s[0], -s[1]);
     }
   }
   return true;

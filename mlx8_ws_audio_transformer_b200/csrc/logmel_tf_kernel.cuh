@@ -68,9 +68,12 @@ constexpr int kTfMaxTiles = 128;
 // stage-1 constants of column pair c = b / 2, packed (b, b + 1); twiddles of k1 = 1..10 at [k1 - 1]
 // (each entry is the 64-bit image of an f32x2: low word = column b, high word = column b + 1, so a
 // constant reaches the FFMA2 as one aligned uniform-register pair without any packing move)
+struct alignas(16) TfPairConsts {      // one column pair: 640 bytes, read with warp-uniform LDS.128
+  unsigned long long w[20], nw[20];
+  unsigned long long twr[10], ntwr[10], twi[10], ntwi[10];
+};
 struct alignas(16) TfTables {
-  unsigned long long w[10][20], nw[10][20];
-  unsigned long long twr[10][10], ntwr[10][10], twi[10][10], ntwi[10][10];
+  TfPairConsts cp[10];
 };
 __host__ __device__ inline unsigned long long tf_pack2(float lo, float hi) {
   unsigned a, b;
@@ -172,31 +175,35 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Stage 2 writes the powers back in place: [pair_base(q) + 2 j + {0, 1}] = P_k(j), P_k'(j).
 __device__ __forceinline__ constexpr int tf_pair_base(int q) { return 20 + 80 * q; }
 
-// one stage-1 codelet: columns (2 CP, 2 CP + 1) of this lane's frame; every table offset and
-// every tensor-memory column is a compile-time constant (uniform-register operands, no index math)
-template <int CP, class TabRef>
-__device__ __forceinline__ void tf_stage1_pair(const TabRef& tab, const float4 (&x4)[20], uint32_t tm) {
+// one stage-1 codelet: the column pair cp = (2 cp, 2 cp + 1) of this lane's frame, taken from the .xy
+// (HALF 0) or .zw (HALF 1) halves of the group's LDS.128 results.  The column pair enters only
+// through the table pointer and two tensor-memory base addresses, so ONE copy of this code serves
+// all ten column pairs (the instruction stream, not the arithmetic, was the cost of unrolling them:
+// 102 KB of code, 8 % of warp time waiting for instructions).
+template <int HALF>
+__device__ __forceinline__ void tf_stage1_pair(const TfPairConsts* __restrict__ c, const float4 (&x4)[20], uint32_t tm2,
+                                               uint32_t tm8) {
   f32x2 x[20], w[20], nw[20], twr[11], ntwr[11], twi[11], ntwi[11], yr[11], yi[11];
 #pragma unroll
   for (int i = 0; i < 20; ++i) {
-    x[i] = (CP & 1) == 0 ? vpack(x4[i].x, x4[i].y) : vpack(x4[i].z, x4[i].w);
-    w[i] = vfrombits(tab.w[CP][i]);
-    nw[i] = vfrombits(tab.nw[CP][i]);
+    x[i] = HALF == 0 ? vpack(x4[i].x, x4[i].y) : vpack(x4[i].z, x4[i].w);
+    w[i] = vfrombits(c->w[i]);
+    nw[i] = vfrombits(c->nw[i]);
   }
   twr[0] = ntwr[0] = twi[0] = ntwi[0] = vzero<f32x2>();     // unused by the codelet
 #pragma unroll
   for (int k = 1; k <= 10; ++k) {
-    twr[k] = vfrombits(tab.twr[CP][k - 1]);
-    ntwr[k] = vfrombits(tab.ntwr[CP][k - 1]);
-    twi[k] = vfrombits(tab.twi[CP][k - 1]);
-    ntwi[k] = vfrombits(tab.ntwi[CP][k - 1]);
+    twr[k] = vfrombits(c->twr[k - 1]);
+    ntwr[k] = vfrombits(c->ntwr[k - 1]);
+    twi[k] = vfrombits(c->twi[k - 1]);
+    ntwi[k] = vfrombits(c->ntwi[k - 1]);
   }
   stage1_r20p<f32x2>(x, w, twr, twi, ntwi, nw, ntwr, yr, yi);
-  tm_st2(tm + 2 * CP, vlo(yr[0]), vhi(yr[0]));
+  tm_st2(tm2, vlo(yr[0]), vhi(yr[0]));                       // row 0: tm + 2 cp
 #pragma unroll
-  for (int q = 0; q < 5; ++q) {
+  for (int q = 0; q < 5; ++q) {                              // row pairs: tm + pair_base(q) + 8 cp
     const int k = 2 * q + 1, k2 = 2 * q + 2;
-    tm_st8v(tm + tf_pair_base(q) + 8 * CP, vlo(yr[k]), vlo(yr[k2]), vlo(yi[k]), vlo(yi[k2]), vhi(yr[k]), vhi(yr[k2]),
+    tm_st8v(tm8 + tf_pair_base(q), vlo(yr[k]), vlo(yr[k2]), vlo(yi[k]), vlo(yi[k2]), vhi(yr[k]), vhi(yr[k2]),
             vhi(yi[k]), vhi(yi[k2]));
   }
 }
@@ -247,9 +254,11 @@ __device__ __forceinline__ void tf_mel_store(uint32_t tm, float* op, long long o
   float acc[P::MAXHALF];
 #pragma unroll
   for (int m = 0; m < P::MAXHALF; ++m) acc[m] = 0.0f;
-  float p0[12], pa[40], pb[40];
+  float p0[12];
   tm_ld8(tm, p0);
   tm_ld4(tm + 8, p0 + 8);
+#ifndef LM_TF_MEL_DEPTH3
+  float pa[40], pb[40];
   tm_ld32(tm + tf_pair_base(0), pa);
   tm_ld8(tm + tf_pair_base(0) + 32, pa + 32);
   tm_wait_ld();
@@ -268,6 +277,29 @@ __device__ __forceinline__ void tf_mel_store(uint32_t tm, float* op, long long o
   LM_TF_PAIR(3, pb, pa)
   LM_TF_PAIR(4, pa, pb)
 #undef LM_TF_PAIR
+#else
+  // three register sets: two row pairs are on their way while one is used
+  float pa[40], pb[40], pc[40];
+  tm_ld32(tm + tf_pair_base(0), pa);
+  tm_ld8(tm + tf_pair_base(0) + 32, pa + 32);
+  tm_wait_ld();
+  tm_ld32(tm + tf_pair_base(1), pb);
+  tm_ld8(tm + tf_pair_base(1) + 32, pb + 32);
+  tf_mel_row0<NM, R>(p0, acc);
+#define LM_TF_PAIR(Q, CUR, NXT2)                                         \
+  if (Q < 3) {                                                           \
+    tm_ld32(tm + tf_pair_base(Q + 2), NXT2);                             \
+    tm_ld8(tm + tf_pair_base(Q + 2) + 32, NXT2 + 32);                    \
+  }                                                                      \
+  tf_mel_pair<NM, Q, R>(CUR, acc);                                       \
+  if (Q < 4) tm_wait_ld();
+  LM_TF_PAIR(0, pa, pc)
+  LM_TF_PAIR(1, pb, pa)
+  LM_TF_PAIR(2, pc, pb)
+  LM_TF_PAIR(3, pa, pc)
+  LM_TF_PAIR(4, pb, pa)
+#undef LM_TF_PAIR
+#endif
   // running maximum / tile minimum of log2(mel): four independent chains of 3-input min / max
   float hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
   op += M0 * ostep;
@@ -435,19 +467,25 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
       // ================= stage 1: wave tile -> Y in tensor memory =================
       {
         const float* mine = tile + fl * G::PITCH;
-        // (a rolled loop over a switch: one basic block per unit keeps ptxas from hoisting the constant
-        //  loads of later column pairs over earlier ones and running out of uniform registers)
-#pragma unroll 1
-        for (int u = 0; u < 3; ++u) {
+        // role A: column groups 0, 1 and the first pair of group 2; role B: the second pair of group 2
+        // and groups 3, 4.  One rolled loop = one copy of the two-codelet group body for both roles.
+        if (role == 1) {
           float4 x4[20];
-          switch (role * 3 + u) {
-            case 0: tf_load_group(mine, 0, x4); tf_stage1_pair<0>(tab, x4, tm); tf_stage1_pair<1>(tab, x4, tm); break;
-            case 1: tf_load_group(mine, 1, x4); tf_stage1_pair<2>(tab, x4, tm); tf_stage1_pair<3>(tab, x4, tm); break;
-            case 2: tf_load_group(mine, 2, x4); tf_stage1_pair<4>(tab, x4, tm); break;
-            case 3: tf_load_group(mine, 2, x4); tf_stage1_pair<5>(tab, x4, tm); break;
-            case 4: tf_load_group(mine, 3, x4); tf_stage1_pair<6>(tab, x4, tm); tf_stage1_pair<7>(tab, x4, tm); break;
-            default: tf_load_group(mine, 4, x4); tf_stage1_pair<8>(tab, x4, tm); tf_stage1_pair<9>(tab, x4, tm); break;
-          }
+          tf_load_group(mine, 2, x4);
+          tf_stage1_pair<1>(&tab.cp[5], x4, tm + 2 * 5, tm + 8 * 5);
+        }
+#pragma unroll 1
+        for (int u = 0; u < 2; ++u) {
+          const int g = role * 3 + u;
+          float4 x4[20];
+          tf_load_group(mine, g, x4);
+          tf_stage1_pair<0>(&tab.cp[2 * g], x4, tm + 4 * g, tm + 16 * g);
+          tf_stage1_pair<1>(&tab.cp[2 * g + 1], x4, tm + 4 * g + 2, tm + 16 * g + 8);
+        }
+        if (role == 0) {
+          float4 x4[20];
+          tf_load_group(mine, 2, x4);
+          tf_stage1_pair<0>(&tab.cp[4], x4, tm + 2 * 4, tm + 8 * 4);
         }
       }
       tm_wait_st();
@@ -531,7 +569,10 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
       if (s_tmin[pair][tt][role] > thr + 1e-5f) continue;   // (a NaN minimum takes the fix-up path)
       if (a.vec_ok && (len & 3) == 0) {
         const int q = len >> 2, j = lane & 7;         // <= 8 float4 per row: four rows per warp pass
-        constexpr int UNR = 8;
+#ifndef LM_TF_FIX_UNR
+#define LM_TF_FIX_UNR 8
+#endif
+        constexpr int UNR = LM_TF_FIX_UNR;
         for (int m0 = mA + (lane >> 3); m0 < mB; m0 += 4 * UNR) {
           float4 v[UNR];
 #pragma unroll
