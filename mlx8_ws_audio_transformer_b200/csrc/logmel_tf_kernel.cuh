@@ -180,13 +180,11 @@ __device__ __forceinline__ constexpr int tf_pair_base(int q) { return 20 + 80 * 
 // through the table pointer and two tensor-memory base addresses, so ONE copy of this code serves
 // all ten column pairs (the instruction stream, not the arithmetic, was the cost of unrolling them:
 // 102 KB of code, 8 % of warp time waiting for instructions).
-template <int HALF>
-__device__ __forceinline__ void tf_stage1_pair(const TfPairConsts* __restrict__ c, const float4 (&x4)[20], uint32_t tm2,
+__device__ __forceinline__ void tf_stage1_pair(const TfPairConsts* __restrict__ c, const f32x2 (&x)[20], uint32_t tm2,
                                                uint32_t tm8) {
-  f32x2 x[20], w[20], nw[20], twr[11], ntwr[11], twi[11], ntwi[11], yr[11], yi[11];
+  f32x2 w[20], nw[20], twr[11], ntwr[11], twi[11], ntwi[11], yr[11], yi[11];
 #pragma unroll
   for (int i = 0; i < 20; ++i) {
-    x[i] = HALF == 0 ? vpack(x4[i].x, x4[i].y) : vpack(x4[i].z, x4[i].w);
     w[i] = vfrombits(c->w[i]);
     nw[i] = vfrombits(c->nw[i]);
   }
@@ -208,11 +206,24 @@ __device__ __forceinline__ void tf_stage1_pair(const TfPairConsts* __restrict__ 
   }
 }
 
-__device__ __forceinline__ void tf_load_group(const float* mine, int g4, float4 (&x4)[20]) {
+// the samples of columns 4 g4 .. 4 g4 + 3 (two column pairs) of this lane's frame: 20 conflict-free LDS.128
+__device__ __forceinline__ void tf_load_group(const float* mine, int g4, f32x2 (&xa)[20], f32x2 (&xb)[20]) {
 #pragma unroll
   for (int i = 0; i < 20; ++i) {
     const int n = 20 * i;       // sample n = 20 i + 4 g4 .. + 3 of the frame; a hop row holds 160 samples + 4 pad
-    x4[i] = *reinterpret_cast<const float4*>(mine + n + 4 * (n / TfGeo::HOP) + 4 * g4);
+    const float4 v = *reinterpret_cast<const float4*>(mine + n + 4 * (n / TfGeo::HOP) + 4 * g4);
+    xa[i] = vpack(v.x, v.y);
+    xb[i] = vpack(v.z, v.w);
+  }
+}
+// one column pair alone (columns 2 cp, 2 cp + 1): 20 LDS.64 -- two-way bank conflicts, i.e. the LSU time
+// of the LDS.128 they replace, for one copy of the code instead of one per half
+__device__ __forceinline__ void tf_load_pair(const float* mine, int cp, f32x2 (&x)[20]) {
+#pragma unroll
+  for (int i = 0; i < 20; ++i) {
+    const int n = 20 * i;
+    const float2 v = *reinterpret_cast<const float2*>(mine + n + 4 * (n / TfGeo::HOP) + 2 * cp);
+    x[i] = vpack(v.x, v.y);
   }
 }
 
@@ -469,23 +480,19 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
         const float* mine = tile + fl * G::PITCH;
         // role A: column groups 0, 1 and the first pair of group 2; role B: the second pair of group 2
         // and groups 3, 4.  One rolled loop = one copy of the two-codelet group body for both roles.
-        if (role == 1) {
-          float4 x4[20];
-          tf_load_group(mine, 2, x4);
-          tf_stage1_pair<1>(&tab.cp[5], x4, tm + 2 * 5, tm + 8 * 5);
-        }
 #pragma unroll 1
         for (int u = 0; u < 2; ++u) {
           const int g = role * 3 + u;
-          float4 x4[20];
-          tf_load_group(mine, g, x4);
-          tf_stage1_pair<0>(&tab.cp[2 * g], x4, tm + 4 * g, tm + 16 * g);
-          tf_stage1_pair<1>(&tab.cp[2 * g + 1], x4, tm + 4 * g + 2, tm + 16 * g + 8);
+          f32x2 xa[20], xb[20];
+          tf_load_group(mine, g, xa, xb);
+          tf_stage1_pair(&tab.cp[2 * g], xa, tm + 4 * g, tm + 16 * g);
+          tf_stage1_pair(&tab.cp[2 * g + 1], xb, tm + 4 * g + 2, tm + 16 * g + 8);
         }
-        if (role == 0) {
-          float4 x4[20];
-          tf_load_group(mine, 2, x4);
-          tf_stage1_pair<0>(&tab.cp[4], x4, tm + 2 * 4, tm + 8 * 4);
+        {
+          const int cp = 4 + role;             // the column pairs of group 2, one per role
+          f32x2 x[20];
+          tf_load_pair(mine, cp, x);
+          tf_stage1_pair(&tab.cp[cp], x, tm + 2 * cp, tm + 8 * cp);
         }
       }
       tm_wait_st();
@@ -511,20 +518,16 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
           tm_st8(tm, p);
           tm_st4(tm + 8, p[8], p[9], p[10], p[11]);
         }
+      }
+      {
+        const int q0 = role ? 2 : 0, q1 = role ? 5 : 2, f0 = role ? 0 : 1;
 #pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-          fetch_rows4(1 + q);
+        for (int q = q0; q < q1; ++q) {        // one copy of the pair codelet for both roles
+          fetch_rows4(f0 + q - q0);
           tf_stage2_pair(tm + (uint32_t)tf_pair_base(q));
         }
         fetch_rows4(3);
-      } else {
-#pragma unroll 1
-        for (int q = 2; q < 5; ++q) {
-          fetch_rows4(q - 2);
-          tf_stage2_pair(tm + (uint32_t)tf_pair_base(q));
-        }
-        fetch_rows4(3);
-        fetch_rows4(4);
+        if (role) fetch_rows4(4);
       }
       cp_async_commit();
       tm_wait_st();
@@ -570,7 +573,7 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
       if (a.vec_ok && (len & 3) == 0) {
         const int q = len >> 2, j = lane & 7;         // <= 8 float4 per row: four rows per warp pass
 #ifndef LM_TF_FIX_UNR
-#define LM_TF_FIX_UNR 8
+#define LM_TF_FIX_UNR 16
 #endif
         constexpr int UNR = LM_TF_FIX_UNR;
         for (int m0 = mA + (lane >> 3); m0 < mB; m0 += 4 * UNR) {
