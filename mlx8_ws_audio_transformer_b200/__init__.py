@@ -7,7 +7,10 @@ Public surface:
 * :class:`MelSpectrogram` / :class:`LogMelSpectrogram` -- ``torchaudio.transforms.MelSpectrogram``
   replacement (``.charles/spectrogram.py:79-87,161-162``);
 * :class:`LogMelFrontend` -- the raw operator over device or host buffers;
-* :class:`ShardedFrontend`, :func:`shard_bounds` -- clip sharding across ranks.
+* :class:`ShardedFrontend`, :func:`shard_bounds` -- clip sharding across ranks;
+* :class:`PinnedFeatureWriter`, :class:`DeviceCollator` -- feature store / collator side
+  (``.charles/spectrogram.py:165-181``, ``AB/fineTune.py:99-118``);
+* :mod:`openai_whisper` -- ``whisper.log_mel_spectrogram`` / ``pad_or_trim`` semantics (``AB/wavToWhisper.py:10-13``).
 
 Heavy imports (torch, transformers) happen on first attribute access, not at package import.
 """
@@ -16,6 +19,7 @@ from __future__ import annotations
 __all__ = [
     "LogMelFrontend", "LogMelWhisperFeatureExtractor", "MelSpectrogram", "LogMelSpectrogram",
     "ShardedFrontend", "shard_bounds", "shard_sizes", "launch_count", "build",
+    "PinnedFeatureWriter", "DeviceCollator", "openai_whisper",
 ]
 
 _LAZY = {
@@ -28,10 +32,16 @@ _LAZY = {
     "shard_bounds": ("sharding", "shard_bounds"),
     "shard_sizes": ("sharding", "shard_sizes"),
     "build": ("_native", "build"),
+    "PinnedFeatureWriter": ("store", "PinnedFeatureWriter"),
+    "DeviceCollator": ("store", "DeviceCollator"),
 }
 
 
 def __getattr__(name):
+    if name == "openai_whisper":
+        import importlib
+
+        return importlib.import_module(f"{__name__}.openai_whisper")
     if name in _LAZY:
         import importlib
 

@@ -222,3 +222,36 @@ def test_out_and_length_arguments_are_validated():
     dev0 = torch.cuda.current_device()
     LogMelFrontend(400, 160, O.slaney_mel_filter_bank(201, 80), N.LOG10_CLAMP_WHISPER_NORM, device=dev0).forward(x)
     assert torch.cuda.current_device() == dev0                                # the library restores the caller's device
+
+
+def test_openai_whisper_log_mel_semantics():
+    """whisper.log_mel_spectrogram (wavToWhisper.py:10-13 -> model.transcribe): whole file + padding, ONE maximum."""
+    from mlx8_ws_audio_transformer_b200 import openai_whisper as W
+    rng = np.random.default_rng(11)
+    audio = (rng.standard_normal(16000 * 47 + 123) * 0.05).astype(np.float32)        # a 47 s "file": longer than one container
+    audio[: 16000 * 3] *= 20.0                                                        # its loud start sets the file's maximum
+    mel = W.log_mel_spectrogram(audio, n_mels=80, padding=W.N_SAMPLES)               # as transcribe() calls it
+    n = len(audio) + W.N_SAMPLES
+    assert mel.is_cuda and mel.shape == (80, n // 160)
+    ref = O.whisper_logmel(np.concatenate([audio, np.zeros(W.N_SAMPLES, np.float32)])[None], n_mels=80, n_samples=n)[0]
+    _parity(mel, ref, "whole file")
+    seg = W.pad_or_trim(mel, W.N_FRAMES)                                              # the first 30 s segment fed to the encoder
+    assert seg.shape == (80, 3000)
+    # the HF container of the same first 30 s has its own (different) maximum: the two frontends are not interchangeable
+    short = W.log_mel_spectrogram(audio[:16000 * 5], n_mels=128)
+    _parity(short, O.whisper_logmel(audio[None, :16000 * 5], n_mels=128, n_samples=16000 * 5)[0], "5 s, 128 mels")
+    assert np.array_equal(W.pad_or_trim(np.arange(5.0), 8), np.array([0, 1, 2, 3, 4, 0, 0, 0.0]))
+    assert W.pad_or_trim(torch.arange(10.0), 4).tolist() == [0, 1, 2, 3]
+
+
+def test_qwen2_audio_extractor_is_the_128_mel_dropin():
+    """Qwen2-Audio's processor (qwen2_audio_tests.py:34,51-52) calls WhisperFeatureExtractor(feature_size=128) with
+    return_attention_mask=True: the drop-in serves it (oracle for the features, HF's formula for the mask)."""
+    fe = LogMelWhisperFeatureExtractor(feature_size=128)
+    rng = np.random.default_rng(5)
+    clips = [(rng.standard_normal(L) * 0.1).astype(np.float32) for L in (480000, 100001, 31)]
+    o = fe(clips, sampling_rate=16000, return_attention_mask=True, padding="max_length", return_tensors="pt")
+    assert o["input_features"].shape == (3, 128, 3000) and o["attention_mask"].shape == (3, 3000)
+    _parity(o["input_features"], O.whisper_logmel(clips, n_mels=128), "qwen2-audio extractor")
+    for i, L in enumerate((480000, 100001, 31)):
+        assert int(o["attention_mask"][i].sum()) == (L + 159) // 160
