@@ -274,7 +274,6 @@ __device__ __forceinline__ void tf_mel_store(uint32_t tm, float* op, long long o
   float p0[12];
   tm_ld8(tm, p0);
   tm_ld4(tm + 8, p0 + 8);
-#ifndef LM_TF_MEL_DEPTH3
   float pa[40], pb[40];
   tm_ld32(tm + tf_pair_base(0), pa);
   tm_ld8(tm + tf_pair_base(0) + 32, pa + 32);
@@ -294,29 +293,6 @@ __device__ __forceinline__ void tf_mel_store(uint32_t tm, float* op, long long o
   LM_TF_PAIR(3, pb, pa)
   LM_TF_PAIR(4, pa, pb)
 #undef LM_TF_PAIR
-#else
-  // three register sets: two row pairs are on their way while one is used
-  float pa[40], pb[40], pc[40];
-  tm_ld32(tm + tf_pair_base(0), pa);
-  tm_ld8(tm + tf_pair_base(0) + 32, pa + 32);
-  tm_wait_ld();
-  tm_ld32(tm + tf_pair_base(1), pb);
-  tm_ld8(tm + tf_pair_base(1) + 32, pb + 32);
-  tf_mel_row0<NM, R>(p0, acc);
-#define LM_TF_PAIR(Q, CUR, NXT2)                                         \
-  if (Q < 3) {                                                           \
-    tm_ld32(tm + tf_pair_base(Q + 2), NXT2);                             \
-    tm_ld8(tm + tf_pair_base(Q + 2) + 32, NXT2 + 32);                    \
-  }                                                                      \
-  tf_mel_pair<NM, Q, R>(CUR, acc);                                       \
-  if (Q < 4) tm_wait_ld();
-  LM_TF_PAIR(0, pa, pc)
-  LM_TF_PAIR(1, pb, pa)
-  LM_TF_PAIR(2, pc, pb)
-  LM_TF_PAIR(3, pa, pc)
-  LM_TF_PAIR(4, pb, pa)
-#undef LM_TF_PAIR
-#endif
   // running maximum / tile minimum of log2(mel): four independent chains of 3-input min / max
   float hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
   op += M0 * ostep;
@@ -328,7 +304,6 @@ __device__ __forceinline__ void tf_mel_store(uint32_t tm, float* op, long long o
     op[m * ostep] = vaffine(l0, q_scale, 1.0f);
     op[(m + 1) * ostep] = vaffine(l1, q_scale, 1.0f);
   }
-#endif
   hi_out = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
   lo_out = fminf(fminf(lo[0], lo[1]), fminf(lo[2], lo[3]));
 }
