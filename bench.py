@@ -489,6 +489,35 @@ def run_ours(args, wl: Workload, rank: int, local_rank: int, world: int):
     e2e_value = world * eb * e_steps / e_el
     e2e_diff = float((hy[:4] - out[:4].cpu()).abs().max())
 
+    # ---- fused 16-bit PCM ingest, a SEPARATE metric: the same clips as int16 mono frames, converted
+    #      in the kernel's tile loader; device-resident and end to end (H2D bytes halve)
+    pcm = None
+    if wl.kind == "whisper" and wl.cfg == 2 and not args.no_extras:
+        xi = (x * 32768.0).clamp_(-32768, 32767).round_().to(torch.int16)          # [B, T] mono PCM
+        fe.forward(xi, out=out)
+        barrier()
+        p_total, _ = time_steps(fe, xi, None, out, max(3, args.steps // 2))
+        p_ms = max_over_ranks(p_total) / max(3, args.steps // 2)
+        same = float((out[:4] - fe.forward((xi[:4].float() / 32768.0))).abs().max())
+        hxi = torch.empty((eb, wl.n_samples), dtype=torch.int16).pin_memory()
+        hxi.copy_(xi[:eb])
+        for _ in range(2):
+            fe.forward_host(hxi, out=hy)
+        barrier()
+        p0 = time.perf_counter()
+        for _ in range(e_steps):
+            fe.forward_host(hxi, out=hy)
+        torch.cuda.synchronize()
+        p_el = max_over_ranks(time.perf_counter() - p0)
+        bpc = wl.n_samples * 2 + wl.n_mels * wl.n_frames * 4
+        pcm = {"value": world * B / (p_ms * 1e-3), "unit": UNIT, "ms_per_step": p_ms, "algorithmic_bytes_per_clip": bpc,
+               "roofline_frac": bpc * B / (p_ms * 1e-3) / 1e9 / load_peak()[0],
+               "max_abs_vs_float_path_on_the_converted_clips": same,
+               "e2e": {"value": world * eb * e_steps / p_el, "unit": UNIT, "h2d_bytes_per_step": eb * wl.n_samples * 2,
+                       "d2h_bytes_per_step": eb * wl.n_mels * wl.n_frames * 4, "api": "lm_forward_host_pcm16"},
+               "input": "the timed batch quantised to int16 mono (what AB/memoToWav.py:19 writes), x / 32768 inside the kernel"}
+        del xi, hxi
+
     # ---- the same kernel on an input where EVERY tile needs the max-8 clamp (noise 80 dB under one burst)
     clamp = None
     if wl.kind == "whisper" and wl.cfg in (2, 5) and not args.no_extras:
@@ -558,6 +587,8 @@ def run_ours(args, wl: Workload, rank: int, local_rank: int, world: int):
         }
         if parity is not None:
             line["parity"] = parity
+        if pcm is not None:
+            line["pcm16_ingest"] = pcm
         if clamp is not None:
             line["clamp_everywhere"] = clamp
         if strong is not None:

@@ -39,6 +39,7 @@
 // cp.async (16-byte chunks, coalesced) in groups between the stage-2 codelets of the current one.
 // Grid: one CTA of 4 pairs per SM (the CTA owns all 512 TMEM columns), no cooperative launch.
 #pragma once
+#include <type_traits>
 #include <cstdint>
 #include <cstring>
 
@@ -58,7 +59,8 @@ struct TfGeo {
   static constexpr int WARPS = 2 * PAIRS;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int Y_COLS = N2 + 2 * N2 * H1;       // 420 TMEM columns per frame
-  static constexpr size_t SMEM = (size_t)PAIRS * TILE_FLOATS * 4;
+  static constexpr int PCM_STAGE_BYTES = SPAN * 4;       // raw 16-bit frames of a tile: 2 channels x 2 bytes at most
+  static constexpr size_t SMEM = (size_t)PAIRS * (TILE_FLOATS * 4 + PCM_STAGE_BYTES);
   // ask for more than half of the SM's shared memory so that two CTAs (each allocating all of
   // TMEM) can never be co-resident
   static constexpr size_t SMEM_REQUEST = SMEM > 120 * 1024 ? SMEM : 120 * 1024;
@@ -334,6 +336,8 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
   const int pair = warp & 3;                 // = TMEM lane quadrant = SM sub-partition of both warps
   const int role = warp >> 2;                // 0: A, 1: B
   float* tile = reinterpret_cast<float*>(smem_raw) + pair * G::TILE_FLOATS;
+  // raw 16-bit PCM of the next tile (fused ingest): lands here by cp.async, converted into `tile` at tile start
+  const uint4* pstage = reinterpret_cast<const uint4*>(smem_raw + G::PAIRS * G::TILE_FLOATS * 4 + pair * G::PCM_STAGE_BYTES);
 
   // ---- the CTA takes the whole tensor memory of its SM: 512 columns x 128 lanes
   if (warp == 0) {
@@ -381,8 +385,28 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
     // stage-2 row.  Tiles that touch a clip edge (reflection) or the zero padding are written by
     // the lanes, row by row, at once.
     const char* fsrc = nullptr;        // interior tile being fetched: this warp's first chunk; else nullptr
+    bool pcm_staged = false;           // the tile being fetched is raw PCM in `pstage` and still has to be converted
+    bool pcm_edge = false;             // ... and touches a clip edge or the padding: only the chunks inside are copied
+    long long pcm_s0 = 0;              // ... its first sample
+    const int spc = a.pcm_channels == 2 ? 4 : 8;               // PCM: samples per 16-byte chunk
+    // PCM: the warps split the tile like the float32 copies do -- role A hop rows 0-15, role B rows 16-33
+    const int pcm_c0 = role ? 16 * G::HOP / spc : 0;                                        // first chunk of this warp
+    const int pcm_cn = role ? (G::SPAN - 16 * G::HOP) / spc : 16 * G::HOP / spc;            // and how many
     auto fetch_rows4 = [&](int blk) {  // rows 4 blk .. 4 blk + 3 of this warp's half (blk 4, role B: rows 32, 33)
       if (!fsrc) return;
+      if (pcm_staged) {                // a quarter of this warp's raw chunks per call (blk 0..3)
+        if (blk >= 4) return;
+        const int per = (pcm_cn + 127) / 128;                   // iterations of 32 lanes per call: 3 mono, 5 or 6 stereo
+        const unsigned dst0 = smem_u32(pstage) + 16 * pcm_c0;
+#pragma unroll 1
+        for (int k = blk * per; k < (blk + 1) * per; ++k) {
+          const int c = lane + 32 * k;
+          const long long n0 = pcm_s0 + (long long)(pcm_c0 + c) * spc;
+          if (c < pcm_cn && (!pcm_edge || (n0 >= 0 && n0 + spc <= valid)))
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16 * c), "l"(fsrc + 16 * c) : "memory");
+        }
+        return;
+      }
       const unsigned rb = (role * 4 + blk) * (4 * G::PITCH * 4);
       const char* src = fsrc + blk * (4 * G::HOP * 4);
       if (blk < 4) {
@@ -394,40 +418,94 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
         if (lane < 28) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_off[1] + rb), "l"(src + 512) : "memory");
       }
     };
+    // Raw PCM in the staging buffer -> float32 samples in the tile, this warp's rows: the sum of the channels times
+    // 2^-15 / channels, exact in float32.  A group is four samples: 8 (mono) or 16 (stereo) staged bytes in, one
+    // 16-byte store out, both conflict-free, at the byte offsets of the float32 copy plan (dst_off).  No I2F (the
+    // quarter-rate conversion pipe): PRMT sign-extends a 16-bit half, adding it to the bit pattern of 1.5 * 2^23 gives
+    // the float 12582912 + s, and one FFMA scales and removes the offset: (12582912 + s) * 2^-15 - 384 = s / 32768.
+    auto sext_lo = [](unsigned w) { int r; asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(r) : "r"(w)); return r; };
+    auto sext_hi = [](unsigned w) { int r; asm("prmt.b32 %0, %1, 0, 0xBB32;" : "=r"(r) : "r"(w)); return r; };
+    auto pcm_group = [&](auto stereo, unsigned src, float (&f)[4]) {       // staged bytes of one group -> four samples
+      if constexpr (decltype(stereo)::value) {
+        unsigned w[4];
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(src));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          f[j] = fmaf(__int_as_float(sext_lo(w[j]) + sext_hi(w[j]) + 0x4B400000), 1.0f / 65536.0f, -192.0f);
+      } else {
+        unsigned w[2];
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(src));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          f[2 * j] = fmaf(__int_as_float(sext_lo(w[j]) + 0x4B400000), 1.0f / 32768.0f, -384.0f);
+          f[2 * j + 1] = fmaf(__int_as_float(sext_hi(w[j]) + 0x4B400000), 1.0f / 32768.0f, -384.0f);
+        }
+      }
+    };
+    auto pcm_convert_tile = [&](auto stereo) {
+      constexpr unsigned GB = decltype(stereo)::value ? 16 : 8;            // staged bytes per group
+      const unsigned src0 = smem_u32(pstage) + (role * 16 * (G::HOP / 4) + lane) * GB;
+      if (!pcm_edge) {
+#pragma unroll 1
+        for (int blk = 0; blk < 4; ++blk) {                                 // four hop rows = 160 groups, five per lane
+          float f[5][4];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) pcm_group(stereo, src0 + (blk * 160 + 32 * j) * GB, f[j]);
+          const unsigned rb = (role * 4 + blk) * (4 * G::PITCH * 4);
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst_off[j] + rb), "f"(f[j][0]), "f"(f[j][1]),
+                         "f"(f[j][2]), "f"(f[j][3]) : "memory");
+        }
+        if (role) {                                                         // rows 32 and 33: 60 groups
+          const unsigned rb = 8 * (4 * G::PITCH * 4);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (j == 0 || lane < 28) {
+              float f[4];
+              pcm_group(stereo, src0 + (4 * 160 + 32 * j) * GB, f);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst_off[j] + rb), "f"(f[0]), "f"(f[1]), "f"(f[2]),
+                           "f"(f[3]) : "memory");
+            }
+          }
+        }
+        return;
+      }
+      // a tile that touches a clip edge or the padding: groups inside the audio were copied, the others are
+      // reflected / zero samples fetched one by one
+      const int g0 = role * 16 * (G::HOP / 4), g1 = role ? G::SPAN / 4 : 16 * (G::HOP / 4);
+#pragma unroll 1
+      for (int g = g0 + lane; g < g1; g += 32) {
+        const int n0 = 4 * g;
+        const long long c0 = pcm_s0 + (n0 / spc) * spc;                     // the 16-byte chunk the group lies in
+        float f[4];
+        if (c0 >= 0 && c0 + spc <= valid) {
+          pcm_group(stereo, smem_u32(pstage) + g * GB, f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f[j] = load_sample_pcm(pptr, a.pcm_channels, (long)(pcm_s0 + n0 + j), a.n_samples, valid);
+        }
+        *reinterpret_cast<float4*>(tile + n0 + 4 * (n0 / G::HOP)) = make_float4(f[0], f[1], f[2], f[3]);
+      }
+    };
+    auto pcm_convert = [&]() {
+      if (spc == 4) pcm_convert_tile(std::true_type{});
+      else pcm_convert_tile(std::false_type{});
+    };
     auto fetch_begin = [&](int t) {
       const long long s0 = tile_s0(t);
       fsrc = nullptr;
+      pcm_staged = false;
       const bool interior = s0 >= 0 && s0 + G::SPAN <= valid;
       if (interior && !pptr) {
         fsrc = reinterpret_cast<const char*>(cptr + s0) + 16 * lane + role * (4 * 4 * G::HOP * 4);
         return;
       }
-      if (interior && a.tma_ok) {
-        // 16-bit PCM (fused ingest): 16-byte chunks = 8 mono samples / 4 stereo frames, converted
-        // (and down-mixed) on their way into the float tile; this warp's half of the tile
-        const int spc = a.pcm_channels == 2 ? 4 : 8;               // samples per chunk
-        const int half = G::SPAN / spc / 2;
-        const uint4* src = reinterpret_cast<const uint4*>(pptr + s0 * a.pcm_channels);
-#pragma unroll 4
-        for (int c = role * half + lane; c < (role + 1) * half; c += 32) {
-          const uint4 v = __ldg(src + c);
-          const unsigned wds[4] = {v.x, v.y, v.z, v.w};
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int lo = (int)(short)(wds[j] & 0xffffu), hi = (int)(short)(wds[j] >> 16);
-            if (spc == 4) {
-              f[j] = pcm_to_float(lo + hi, 2);
-            } else {
-              f[2 * j] = pcm_to_float(lo, 1);
-              f[2 * j + 1] = pcm_to_float(hi, 1);
-            }
-          }
-          const int n0 = c * spc;                                   // first sample of the chunk (never straddles a hop row)
-          float* d = tile + n0 + 4 * (n0 / G::HOP);
-          *reinterpret_cast<float4*>(d) = make_float4(f[0], f[1], f[2], f[3]);
-          if (spc == 8) *reinterpret_cast<float4*>(d + 4) = make_float4(f[4], f[5], f[6], f[7]);
-        }
+      if (pptr && a.tma_ok) {          // 16-bit PCM (fused ingest): the raw frames go to the staging buffer
+        fsrc = reinterpret_cast<const char*>(pptr + s0 * a.pcm_channels) + 16 * pcm_c0;
+        pcm_staged = true;
+        pcm_edge = !interior;
+        pcm_s0 = s0;
         return;
       }
 #pragma unroll 1
@@ -453,6 +531,14 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
     }
     while (t < T) {
       cp_async_wait_all();
+      if (pcm_staged) {          // (16-bit PCM input only) the raw frames this warp copied -> its rows of the float tile,
+        __syncwarp();            //  which has been dead since the stage-1 barrier of the previous tile
+        pcm_convert();
+#ifdef LM_DBG_CONVERT2
+        __syncwarp();
+        pcm_convert();
+#endif
+      }
       pair_sync(pair);           // the tile is complete; the partner has finished reading P of the previous tile
       // Lanes past the clip's last frame (only in its last tile) redo the last valid frame: same
       // samples, same arithmetic, the same value stored to the same address -- no predicates anywhere.
