@@ -498,7 +498,8 @@ def run_ours(args, wl: Workload, rank: int, local_rank: int, world: int):
         barrier()
         p_total, _ = time_steps(fe, xi, None, out, max(3, args.steps // 2))
         p_ms = max_over_ranks(p_total) / max(3, args.steps // 2)
-        same = float((out[:4] - fe.forward((xi[:4].float() / 32768.0))).abs().max())
+        nb = min(B, 640)                 # enough clips for the float32 launch to take the same kernel as the timed one
+        same = float((out[:4] - fe.forward(xi[:nb].float() / 32768.0)[:4]).abs().max())
         hxi = torch.empty((eb, wl.n_samples), dtype=torch.int16).pin_memory()
         hxi.copy_(xi[:eb])
         for _ in range(2):
@@ -512,7 +513,7 @@ def run_ours(args, wl: Workload, rank: int, local_rank: int, world: int):
         bpc = wl.n_samples * 2 + wl.n_mels * wl.n_frames * 4
         pcm = {"value": world * B / (p_ms * 1e-3), "unit": UNIT, "ms_per_step": p_ms, "algorithmic_bytes_per_clip": bpc,
                "roofline_frac": bpc * B / (p_ms * 1e-3) / 1e9 / load_peak()[0],
-               "max_abs_vs_float_path_on_the_converted_clips": same,
+               "max_abs_vs_float32_path_on_the_converted_clips": same,
                "e2e": {"value": world * eb * e_steps / p_el, "unit": UNIT, "h2d_bytes_per_step": eb * wl.n_samples * 2,
                        "d2h_bytes_per_step": eb * wl.n_mels * wl.n_frames * 4, "api": "lm_forward_host_pcm16"},
                "input": "the timed batch quantised to int16 mono (what AB/memoToWav.py:19 writes), x / 32768 inside the kernel"}

@@ -396,14 +396,23 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
       if (!fsrc) return;
       if (pcm_staged) {                // a quarter of this warp's raw chunks per call (blk 0..3)
         if (blk >= 4) return;
-        const int per = (pcm_cn + 127) / 128;                   // iterations of 32 lanes per call: 3 mono, 5 or 6 stereo
-        const unsigned dst0 = smem_u32(pstage) + 16 * pcm_c0;
+        const int per = spc == 8 ? 3 : 6;                       // 32-lane rounds per call: 12 (mono) / 24 (stereo) cover 350 / 700
+        const unsigned dst = smem_u32(pstage) + 16 * (pcm_c0 + lane);
+        if (!pcm_edge) {               // fsrc already points at this lane's first chunk
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int k = blk * per + i;
+            if (i < per && lane + 32 * k < pcm_cn)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512 * k), "l"(fsrc + 512 * k) : "memory");
+          }
+          return;
+        }
 #pragma unroll 1
-        for (int k = blk * per; k < (blk + 1) * per; ++k) {
+        for (int k = blk * per; k < (blk + 1) * per; ++k) {     // a tile at a clip edge: only the chunks inside the audio
           const int c = lane + 32 * k;
           const long long n0 = pcm_s0 + (long long)(pcm_c0 + c) * spc;
-          if (c < pcm_cn && (!pcm_edge || (n0 >= 0 && n0 + spc <= valid)))
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16 * c), "l"(fsrc + 16 * c) : "memory");
+          if (c < pcm_cn && n0 >= 0 && n0 + spc <= valid)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512 * k), "l"(fsrc + 512 * k) : "memory");
         }
         return;
       }
@@ -421,8 +430,9 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
     // Raw PCM in the staging buffer -> float32 samples in the tile, this warp's rows: the sum of the channels times
     // 2^-15 / channels, exact in float32.  A group is four samples: 8 (mono) or 16 (stereo) staged bytes in, one
     // 16-byte store out, both conflict-free, at the byte offsets of the float32 copy plan (dst_off).  No I2F (the
-    // quarter-rate conversion pipe): PRMT sign-extends a 16-bit half, adding it to the bit pattern of 1.5 * 2^23 gives
-    // the float 12582912 + s, and one FFMA scales and removes the offset: (12582912 + s) * 2^-15 - 384 = s / 32768.
+    // quarter-rate conversion pipe): the integer is placed in the mantissa of 1.5 * 2^23, which gives the float
+    // 12582912 + s, and one FFMA scales and removes the offset: (12582912 + s) * 2^-15 - 384 = s / 32768.  Stereo:
+    // PRMT sign-extends the halves, one three-input add sums them onto the bit pattern.
     auto sext_lo = [](unsigned w) { int r; asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(r) : "r"(w)); return r; };
     auto sext_hi = [](unsigned w) { int r; asm("prmt.b32 %0, %1, 0, 0xBB32;" : "=r"(r) : "r"(w)); return r; };
     auto pcm_group = [&](auto stereo, unsigned src, float (&f)[4]) {       // staged bytes of one group -> four samples
@@ -435,10 +445,13 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
       } else {
         unsigned w[2];
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(src));
+        // mono, three ALU operations per two samples: flipping bit 15 of both halves turns s into the unsigned
+        // s + 32768, which is then spliced under the exponent of 1.5 * 2^23 (LOP3 / PRMT) -- offset 385 instead of 384
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          f[2 * j] = fmaf(__int_as_float(sext_lo(w[j]) + 0x4B400000), 1.0f / 32768.0f, -384.0f);
-          f[2 * j + 1] = fmaf(__int_as_float(sext_hi(w[j]) + 0x4B400000), 1.0f / 32768.0f, -384.0f);
+          const unsigned u = w[j] ^ 0x80008000u;
+          f[2 * j] = fmaf(__uint_as_float((u & 0xffffu) | 0x4B400000u), 1.0f / 32768.0f, -385.0f);
+          f[2 * j + 1] = fmaf(__uint_as_float(__byte_perm(u, 0x4B400000u, 0x7632)), 1.0f / 32768.0f, -385.0f);
         }
       }
     };
@@ -502,7 +515,7 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
         return;
       }
       if (pptr && a.tma_ok) {          // 16-bit PCM (fused ingest): the raw frames go to the staging buffer
-        fsrc = reinterpret_cast<const char*>(pptr + s0 * a.pcm_channels) + 16 * pcm_c0;
+        fsrc = reinterpret_cast<const char*>(pptr + s0 * a.pcm_channels) + 16 * (pcm_c0 + lane);
         pcm_staged = true;
         pcm_edge = !interior;
         pcm_s0 = s0;

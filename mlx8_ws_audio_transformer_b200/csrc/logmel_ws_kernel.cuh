@@ -31,16 +31,6 @@
 #pragma once
 #include "logmel_kernel.cuh"
 
-// Cycles by which the FFT warps with the lighter stage-1 load (two tasks instead of three) start
-// stage 1 late.  All FFT warps leave the same barrier and run the same load -> math -> store
-// sequence, so without an offset the two warps of a sub-partition ask for the LSU at the same time
-// and for the FP32 pipe at the same time.  Measured with one CTA per clip, ms per 4096 clips:
-// 0: 5.66, 100: 5.56, 200: 5.45, 250: 5.48, 350: 5.51, 500: 5.52 (650+: the delayed warps become
-// the critical path).
-#ifndef LM_STAGGER1
-#define LM_STAGGER1 200
-#endif
-
 namespace lm {
 
 enum : int { BAR_PFULL0 = 1, BAR_PFULL1 = 2, BAR_PEMPTY0 = 3, BAR_PEMPTY1 = 4, BAR_YDONE = 5, BAR_S2DONE = 6,
@@ -135,12 +125,6 @@ logmel_ws_kernel(const __grid_constant__ Tables<G> tab, const KArgs a) {
         LM_STAMP(1)
         if (i >= 2) nbar_sync((i & 1) ? BAR_PEMPTY1 : BAR_PEMPTY0, NT);   // mel(i - 2) has left this plane
         T* Yre = Yre0 + (i & 1) * G::YRE_ELEMS;
-#if LM_STAGGER1 > 0
-        if (tab.s1_tasks[warp][G::S1_MAX - 1] < 0) {           // a warp with spare time in this phase
-          const long long c0 = clock64();
-          while (clock64() - c0 < LM_STAGGER1) {}
-        }
-#endif
 #pragma unroll 1
         for (int k = 0; k < G::S1_MAX; ++k) {
           const int task = tab.s1_tasks[warp][k];
