@@ -110,7 +110,7 @@ struct lm_handle {
 
 int TfLauncher::launch(const lm::KArgs& a, cudaStream_t st) {
   void* args[] = {(void*)&tab, (void*)&a};
-  const int grid = (int)std::min<long long>(n_sm, (a.batch + lm::TfGeo::PAIRS - 1) / lm::TfGeo::PAIRS);
+  const int grid = (int)std::min<long long>(n_sm, a.batch);   // clips spread over the SMs first (pair p of CTA c: clip p * grid + c)
   cudaError_t e = cudaLaunchKernel(a.n_frames == 3000 ? kernel3000 : kernel, dim3(grid), dim3(lm::TfGeo::THREADS), args,
                                    lm::TfGeo::SMEM_REQUEST, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel(logmel_tf_kernel)");
@@ -237,9 +237,9 @@ int attach_tf(lm_handle* h, const lm_config* cfg, const float* window) {
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t->kernel, lm::TfGeo::THREADS, lm::TfGeo::SMEM_REQUEST));
   if (occ != 1) return fail(LM_ERR_NO_DEVICE, "thread-per-frame kernel: %d CTAs per SM (expected exactly 1: the CTA owns all of TMEM)", occ);
   h->tf = std::move(t);
-  // every warp pair of the grid (4 per SM) should own at least one clip; below that the CTA-tiled
-  // kernel, which spreads a clip over many CTAs, is faster
-  h->tf_min_batch = (long long)h->n_sm * lm::TfGeo::PAIRS;
+  // three of the four warp pairs of every SM should own a clip; below that the CTA-tiled kernel, which
+  // spreads a clip over many CTAs, is faster (profiles/r02_dispatch_sweep.txt: 444 clips 606 vs 650 us)
+  h->tf_min_batch = (long long)h->n_sm * (lm::TfGeo::PAIRS - 1);
   if (const char* e = std::getenv("LM_TF_MIN_BATCH")) h->tf_min_batch = std::max(1, atoi(e));   // tuning knob
   return 0;
 }

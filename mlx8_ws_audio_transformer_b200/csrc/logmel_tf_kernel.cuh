@@ -238,10 +238,13 @@ __device__ __forceinline__ void tf_load_pair(const float* mine, int cp, f32x2 (&
 // one row pair of stage 2: 80 columns in, two complex DFT-20 + |X|^2 as one packed codelet, 40 columns
 // out (in place).  For the pair (9, 10) row 10 runs through the general codelet as well; its outputs
 // j >= 10 repeat bins it already has and are not used.
-__device__ __forceinline__ void tf_stage2_pair(uint32_t base) {
+// `between` runs while the tensor-memory loads are in flight (the cp.async issue of the next tile).
+template <class Between>
+__device__ __forceinline__ void tf_stage2_pair(uint32_t base, Between between) {
   float y[80];
   tm_ld64(base, y);
   tm_ld16(base + 64, y + 64);
+  between();
   tm_wait_ld();
   f32x2 yr[20], yi[20], p[20];
 #pragma unroll
@@ -529,8 +532,11 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
         if (sr >= 0 && sr + len <= valid && !pptr) {
           for (int c = lane; c < len / 4; c += 32) cp_async16(drow + 4 * c, cptr + sr + 4 * c);
         } else {
-          for (int i = lane; i < len; i += 32)
-            drow[i] = load_sample_any(cptr, pptr, a.pcm_channels, (long)(sr + i), a.n_samples, valid);
+#pragma unroll
+          for (int k = 0; k < G::HOP / 32; ++k) {            // the row's loads go out back to back
+            const int i = lane + 32 * k;
+            if (i < len) drow[i] = load_sample_any(cptr, pptr, a.pcm_channels, (long)(sr + i), a.n_samples, valid);
+          }
         }
       }
     };
@@ -604,8 +610,7 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
         const int q0 = role ? 2 : 0, q1 = role ? 5 : 2, f0 = role ? 0 : 1;
 #pragma unroll 1
         for (int q = q0; q < q1; ++q) {        // one copy of the pair codelet for both roles
-          fetch_rows4(f0 + q - q0);
-          tf_stage2_pair(tm + (uint32_t)tf_pair_base(q));
+          tf_stage2_pair(tm + (uint32_t)tf_pair_base(q), [&]() { fetch_rows4(f0 + q - q0); });
         }
         fetch_rows4(3);
         if (role) fetch_rows4(4);
