@@ -214,8 +214,52 @@ def test_full_size_properties():
     ref = O.whisper_logmel(x[sub].cpu().numpy(), n_mels=128)
     _assert_parity(y[sub], ref, "subset")
     assert torch.equal(fe.forward(x[592:]), y[592:])               # contiguous shard == slice of the whole
+    # the dispatch threshold: three clips per SM take the thread-per-frame kernel (one warp pair per SM idle)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    assert "logmel_tf_kernel" in fe.kernel_name(3 * n_sm, 480000) and "logmel_ws_kernel" in fe.kernel_name(3 * n_sm - 1, 480000)
+    assert torch.equal(fe.forward(x[5:5 + 3 * n_sm]), y[5:5 + 3 * n_sm])
     # a shard small enough for the CTA-tiled kernel agrees to float32 rounding, not bit for bit
     assert (fe.forward(x[:40]) - y[:40]).abs().max() < 2e-6
+
+
+@pytest.mark.parametrize("kind", ["float32", "pcm16", "pcm16_stereo"])
+def test_guard_bands_thread_per_frame_kernel(fronts, kind):
+    """(compute-sanitizer is not available on the GPU pool.)  Output and clip-max buffers sit inside larger
+    allocations filled with a sentinel, the waveform rows are followed by NaN / extreme padding that `lengths`
+    hides: nothing outside the buffers may change, nothing from the padding may reach the features.  700 ragged
+    clips of 3.3 s -> the thread-per-frame kernel, run-time frame count, clip-edge and all-padding tiles."""
+    fe = fronts(80, 3)
+    B, T, stride = 700, 52800, 52800 + 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    lengths = torch.randint(0, T + 1, (B,), generator=g, device="cuda", dtype=torch.int32)
+    lengths[:4] = torch.tensor([0, 1, T, 399], dtype=torch.int32)
+    clean = torch.randn(B, T, generator=g, device="cuda") * 0.2
+    mask = torch.arange(T, device="cuda")[None, :] < lengths[:, None]
+    if kind == "float32":
+        buf = torch.full((B, stride), float("nan"), device="cuda")
+        buf[:, :T] = torch.where(mask, clean, torch.full_like(clean, float("nan")))
+        x = buf[:, :T]                                             # row stride 52864 floats, 16-byte aligned rows
+        want = fe.forward(torch.where(mask, clean, torch.zeros_like(clean)))
+    else:
+        ch = 2 if kind == "pcm16_stereo" else 1
+        pcm = (torch.randn(B, T, ch, generator=g, device="cuda") * 6000).clamp_(-32768, 32767).to(torch.int16)
+        m3 = mask[:, :, None].expand(B, T, ch)
+        buf = torch.full((B, stride, ch), 32767, device="cuda", dtype=torch.int16)
+        buf[:, :T] = torch.where(m3, pcm, torch.full_like(pcm, -32768))
+        x = buf[:, :T] if ch == 2 else buf[:, :T, 0]
+        mono = torch.where(m3, pcm, torch.zeros_like(pcm)).float().sum(-1) / (32768.0 * ch)
+        want = fe.forward(mono)
+    n_frames = T // 160
+    SENT = 1234.5
+    big = torch.full((B + 2, 80, n_frames), SENT, device="cuda")
+    cm = torch.full((B + 2,), SENT, device="cuda")
+    assert "logmel_tf_kernel<80, 0>" in fe.kernel_name(B, T)
+    got = fe.forward(x, lengths=lengths, out=big[1:B + 1], clip_max=cm[1:B + 1])
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert torch.equal(got, want)
+    assert (big[0] == SENT).all() and (big[B + 1] == SENT).all()
+    assert cm[0] == SENT and cm[B + 1] == SENT and torch.isfinite(cm[1:B + 1]).all()
 
 
 @pytest.mark.parametrize("nm", [80, 128])
