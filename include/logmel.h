@@ -138,7 +138,9 @@ int lm_host_register(void* p, size_t bytes);
 int lm_host_unregister(void* p);
 
 /* Introspection used by bench.py / tests: number of kernels launched by this library in the
- * calling process, SM count and resident CTAs of the forward kernel, dynamic shared memory. */
+ * calling process; SM count, resident CTAs, dynamic shared memory, threads and frames per tile of the
+ * handle's CTA-tiled kernel (the thread-per-frame kernel, when lm_kernel_name says a launch takes it, is
+ * always one 256-thread CTA per SM with 32-frame tiles). */
 int64_t lm_launch_count(void);
 int lm_kernel_info(const lm_handle* h, int32_t* n_sm, int32_t* ctas_per_sm, int32_t* smem_bytes,
                    int32_t* threads, int32_t* frames_per_tile);
