@@ -322,7 +322,15 @@ class Codelet:
             for a in n.args:
                 if isinstance(a, Node):
                     stack.append(a)
-        return [n for n in self.g.order if n.id in live]
+        nodes = [n for n in self.g.order if n.id in live]
+        if ORDER == "level":
+            # experiment: emit by dependency level (all operations whose operands are ready first), i.e. with the
+            # largest distance between dependent instructions; same operations, same results, another schedule
+            level = {}
+            for n in nodes:
+                level[n.id] = 0 if n.op == "in" else 1 + max(level[a.id] for a in n.args if isinstance(a, Node))
+            nodes.sort(key=lambda n: (level[n.id], n.id))
+        return nodes
 
     def op_counts(self):
         cnt = {}
@@ -391,6 +399,9 @@ class Codelet:
                 lines.append(f"  {cexpr} = vneg({v.n.name});")
         lines.append("}")
         return "\n".join(lines)
+
+
+ORDER = "trace"        # "trace": creation order of the symbolic trace (depth first); "level": see live_nodes
 
 
 def _lit(k: float) -> str:
@@ -532,6 +543,9 @@ def selftest():
 
 
 def main():
+    global ORDER
+    if "--level-order" in sys.argv:
+        ORDER = "level"
     if "--selftest" in sys.argv:
         sys.exit(0 if selftest() else 1)
     print(HEADER)
