@@ -73,7 +73,7 @@ typedef struct lm_config {
                                 0: emit 1 + n_samples/hop frames (torchaudio)                     */
   int32_t device;            /* CUDA device ordinal                                               */
   int32_t variant;           /* 0 = default: for the Whisper normalisation with the 80- / 128-filter
-                                Slaney bank, batches of >= 4 clips per SM run the thread-per-frame
+                                Slaney bank, batches of >= 2/3 clip per SM run the thread-per-frame
                                 kernel (tensor memory as transpose scratch), everything else the
                                 CTA-tiled kernels (n_fft 400: warp-specialised CTA, two frames per lane);
                                 1 = CTA-tiled, one frame per lane (scalar FP32 path), 2 = CTA-tiled,

@@ -102,6 +102,7 @@ struct lm_handle {
   HostPipe pipe;
   std::unique_ptr<TfLauncher> tf;
   long long tf_min_batch = 0;        // smallest batch routed to the thread-per-frame kernel
+  int tf_pairs_forced = 0;           // tuning knob LM_TF_PAIRS_PER_CLIP: 1 or 4 warp pairs per clip, 0 = by cost
   std::string tiled_name;            // the CTA-tiled kernel of this handle, as profilers print it
   int ctas_per_clip = 1;             // CTA-tiled kernels, steady state (tuning knob LM_CTAS_PER_CLIP)
   virtual ~lm_handle() {}
@@ -237,10 +238,12 @@ int attach_tf(lm_handle* h, const lm_config* cfg, const float* window) {
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t->kernel, lm::TfGeo::THREADS, lm::TfGeo::SMEM_REQUEST));
   if (occ != 1) return fail(LM_ERR_NO_DEVICE, "thread-per-frame kernel: %d CTAs per SM (expected exactly 1: the CTA owns all of TMEM)", occ);
   h->tf = std::move(t);
-  // three of the four warp pairs of every SM should own a clip; below that the CTA-tiled kernel, which
-  // spreads a clip over many CTAs, is faster (profiles/r02_dispatch_sweep.txt: 444 clips 606 vs 650 us)
-  h->tf_min_batch = (long long)h->n_sm * (lm::TfGeo::PAIRS - 1);
+  // with a clip per CTA (tf_pairs_per_clip) one round of the kernel costs a quarter clip, ~150 us for 30 s of audio;
+  // the CTA-tiled kernel, which spreads a clip over many CTAs, is faster only while most SMs would have no clip
+  // (profiles/r02_dispatch_sweep.txt: 74 clips 120 vs 144 us, 148 clips 214 vs 156 us)
+  h->tf_min_batch = (long long)h->n_sm * 2 / 3;
   if (const char* e = std::getenv("LM_TF_MIN_BATCH")) h->tf_min_batch = std::max(1, atoi(e));   // tuning knob
+  if (const char* e = std::getenv("LM_TF_PAIRS_PER_CLIP")) h->tf_pairs_forced = atoi(e) == 4 ? 4 : atoi(e) == 1 ? 1 : 0;
   return 0;
 }
 
@@ -252,6 +255,18 @@ int64_t frames_for(const lm_config& c, int64_t n_samples) {
 // aligned (cp.async), the batch gives every warp pair a clip and a clip has at most kTfMaxTiles tiles
 bool use_tf(const lm_handle* h, int64_t batch, int64_t n_frames, bool aligned) {
   return h->tf && aligned && batch >= h->tf_min_batch && (n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F <= lm::kTfMaxTiles;
+}
+
+// Thread-per-frame kernel: a clip per warp pair, or a clip per CTA with a quarter of its tiles per pair?  In tile
+// periods: whole clips go round by round over 4 n_sm pairs, quarter clips over n_sm CTAs; the second pays one CTA
+// barrier per clip and the slower clip-edge tiles inside one quarter (2 % here), so it is taken only when it saves
+// a round: mid-size batches (8192 clips over 8 GPUs: 1024 = 1.73 rounds of pairs, but 6.92 of CTAs).
+int tf_pairs_per_clip(const lm_handle* h, int64_t batch, int tiles) {
+  if (h->tf_pairs_forced) return h->tf_pairs_forced;
+  const int64_t P = lm::TfGeo::PAIRS, n = h->n_sm;
+  const int64_t by_pair = ((batch + n * P - 1) / (n * P)) * tiles;
+  const int64_t by_cta = ((batch + n - 1) / n) * ((tiles + P - 1) / P);
+  return by_cta * 102 < by_pair * 100 ? (int)P : 1;
 }
 
 void choose_grid(const lm_handle* h, int64_t batch, int tiles, int* group, int* n_groups) {
@@ -442,6 +457,8 @@ int forward_impl(lm_handle* h, const float* d_wave, const int16_t* d_pcm, int ch
   int rc;
   if (use_tf(h, batch, n_frames, aligned)) {
     a.tiles_per_clip = (int)((n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F);
+    a.group = tf_pairs_per_clip(h, batch, a.tiles_per_clip);
+    a.n_groups = 0;
     rc = h->tf->launch(a, st);
   } else {
     if (d_pcm) a.tma_ok = 0;

@@ -332,7 +332,7 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_tmem;
   __shared__ float s_tmin[G::PAIRS][kTfMaxTiles][2];
-  __shared__ float s_pmax[G::PAIRS][2];
+  __shared__ float s_pmax[2][G::PAIRS][2];
 
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -368,9 +368,17 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
     dst_off[j] = smem_u32(tile) + (unsigned)((i / 40) * G::PITCH * 4 + (i % 40) * 16);
   }
 
-  const int gp = pair * gridDim.x + blockIdx.x;                     // pairs of an SM take clips 148 apart
-  const int gn = gridDim.x * G::PAIRS;
-  for (int clip = gp; clip < a.batch; clip += gn) {
+  // Two ways to hand out the work (a.group, chosen by the host from the batch size): a clip per warp pair (1: the
+  // steady state of a large batch; pairs of an SM take clips 148 apart), or a clip per CTA (4: its four pairs take a
+  // quarter of the tiles each and agree on the clip maximum through shared memory) -- the second wastes at most one
+  // quarter-clip per SM where the first can waste a whole clip per pair, which is what mid-size batches need.
+  const bool coop = a.group == G::PAIRS;
+  const int gp = coop ? blockIdx.x : pair * gridDim.x + blockIdx.x;
+  const int gn = coop ? gridDim.x : gridDim.x * G::PAIRS;
+  const int tq = (T + G::PAIRS - 1) / G::PAIRS;
+  const int t0 = coop ? min(pair * tq, T) : 0, t1 = coop ? min((pair + 1) * tq, T) : T;   // this pair's tiles
+  int par = 0;                                                       // clip parity: s_pmax is double-buffered
+  for (int clip = gp; clip < a.batch; clip += gn, par ^= 1) {
     const float* cptr = a.wave + (long long)clip * a.clip_stride;
     const short* pptr = a.pcm ? a.pcm + (long long)clip * a.clip_stride * a.pcm_channels : nullptr;
     int valid = a.n_samples;
@@ -378,7 +386,7 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
     float* oc = a.out + (long long)clip * NM * n_frames;
     float rmax = -INFINITY;                   // of log2(mel), this warp's filters
     auto next_loud = [&](int t) {
-      while (t < T && tile_is_silent<G>(tile_s0(t), a.n_samples, valid)) ++t;
+      while (t < t1 && tile_is_silent<G>(tile_s0(t), a.n_samples, valid)) ++t;
       return t;
     };
     // Filling the pair's waveform tile (dead at that point) with tile t, half of it per warp.  Hop rows
@@ -541,14 +549,14 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
       }
     };
 
-    int t = next_loud(0);
-    if (t < T) {
+    int t = next_loud(t0);
+    if (t < t1) {
       fetch_begin(t);
 #pragma unroll 1
       for (int blk = 0; blk < 5; ++blk) fetch_rows4(blk);
       cp_async_commit();
     }
-    while (t < T) {
+    while (t < t1) {
       cp_async_wait_all();
       if (pcm_staged) {          // (16-bit PCM input only) the raw frames this warp copied -> its rows of the float tile,
         __syncwarp();            //  which has been dead since the stage-1 barrier of the previous tile
@@ -586,7 +594,7 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
       pair_sync(pair);           // Y is complete, the waveform tile is dead
       const int tn = next_loud(t + 1);
       fsrc = nullptr;
-      if (tn < T) fetch_begin(tn);   // the copies themselves go out between the stage-2 rows
+      if (tn < t1) fetch_begin(tn);  // the copies themselves go out between the stage-2 rows
 
       // ================= stage 2: rows of Y -> |X|^2, in place =================
       // (role A: row 0 and row pairs 0, 1; role B: row pairs 2, 3, 4; the cp.async groups of the next
@@ -636,14 +644,21 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
     // ================= the clip is complete: max - 8 clamp where it bites =================
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-    if (lane == 0) s_pmax[pair][role] = rmax * log_scale;
-    pair_sync(pair);
-    const float cmax = fmaxf(fmaxf(s_pmax[pair][0], s_pmax[pair][1]), silent_val);   // the clamp at `floor`, applied to the maximum
-    if (role == 0 && lane == 0 && a.clip_max) a.clip_max[clip] = cmax;
+    if (lane == 0) s_pmax[par][pair][role] = rmax * log_scale;
+    float cmax = silent_val;                                          // the clamp at `floor`, applied to the maximum
+    if (coop) {                  // all eight warps walk the same clips: a CTA barrier is safe here
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < G::PAIRS; ++q) cmax = fmaxf(cmax, fmaxf(s_pmax[par][q][0], s_pmax[par][q][1]));
+    } else {
+      pair_sync(pair);
+      cmax = fmaxf(cmax, fmaxf(s_pmax[par][pair][0], s_pmax[par][pair][1]));
+    }
+    if (role == 0 && lane == 0 && a.clip_max && (!coop || pair == 0)) a.clip_max[clip] = cmax;
     const float thr = fmaxf(cmax - 8.0f, silent_val);
     const float cval = vaffine(thr, 0.25f, 1.0f);
     const int mA = role == 0 ? 0 : MP::M0, mB = role == 0 ? MP::M0 : NM;            // this warp's filters
-    for (int tt = 0; tt < T; ++tt) {
+    for (int tt = t0; tt < t1; ++tt) {
       const int fa = tt * G::F;
       const int len = min(fa + G::F, n_frames) - fa;
       if (tile_is_silent<G>(tile_s0(tt), a.n_samples, valid)) {

@@ -214,10 +214,13 @@ def test_full_size_properties():
     ref = O.whisper_logmel(x[sub].cpu().numpy(), n_mels=128)
     _assert_parity(y[sub], ref, "subset")
     assert torch.equal(fe.forward(x[592:]), y[592:])               # contiguous shard == slice of the whole
-    # the dispatch threshold: three clips per SM take the thread-per-frame kernel (one warp pair per SM idle)
+    # the dispatch threshold (2/3 clip per SM) and the clip-per-CTA work distribution mid-size batches take:
+    # 1184 clips went a clip per warp pair, these go a clip per CTA -- same kernel, same bits
     n_sm = torch.cuda.get_device_properties(0).multi_processor_count
-    assert "logmel_tf_kernel" in fe.kernel_name(3 * n_sm, 480000) and "logmel_ws_kernel" in fe.kernel_name(3 * n_sm - 1, 480000)
-    assert torch.equal(fe.forward(x[5:5 + 3 * n_sm]), y[5:5 + 3 * n_sm])
+    thr = 2 * n_sm // 3
+    assert "logmel_tf_kernel" in fe.kernel_name(thr, 480000) and "logmel_ws_kernel" in fe.kernel_name(thr - 1, 480000)
+    for nb in (thr, n_sm + 3, 4 * n_sm + 8):
+        assert torch.equal(fe.forward(x[5:5 + nb]), y[5:5 + nb]), nb
     # a shard small enough for the CTA-tiled kernel agrees to float32 rounding, not bit for bit
     assert (fe.forward(x[:40]) - y[:40]).abs().max() < 2e-6
 
@@ -263,12 +266,19 @@ def test_guard_bands_thread_per_frame_kernel(fronts, kind):
 
 
 @pytest.mark.parametrize("nm", [80, 128])
-@pytest.mark.parametrize("variant", [0, 3])
-def test_clamp_everywhere_one_cta_per_clip(nm, variant):
+@pytest.mark.parametrize("how", ["auto", "cta_tiled", "clip_per_pair", "clip_per_cta"])
+def test_clamp_everywhere_one_cta_per_clip(nm, how, monkeypatch):
     """> 148 clips (every CTA / warp pair owns whole clips) whose quiet parts lie > 80 dB under one loud
-    burst: every tile is revisited by the max-8 pass after the clip maximum is known."""
+    burst: every tile is revisited by the max-8 pass after the clip maximum is known.  Run on the CTA-tiled
+    kernel and on the thread-per-frame kernel with both of its work distributions (the knob is read at lm_create)."""
+    variant = 0 if how in ("auto", "cta_tiled") else 3
+    if how == "cta_tiled":
+        monkeypatch.setenv("LM_TF_MIN_BATCH", "1000000000")          # the warp-specialised CTA-tiled kernel
+    if how.startswith("clip_per"):
+        monkeypatch.setenv("LM_TF_PAIRS_PER_CLIP", "1" if how == "clip_per_pair" else "4")
     fe = LogMelFrontend(400, 160, O.slaney_mel_filter_bank(201, nm), N.LOG10_CLAMP_WHISPER_NORM, 1e-10, True,
                         variant=variant)
+    assert ("logmel_tf_kernel" in fe.kernel_name(300, 480000)) == (how != "cta_tiled")
     B = 300
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.randn(B, 480000, generator=g, device="cuda") * 1e-5
