@@ -103,6 +103,7 @@ struct lm_handle {
   std::unique_ptr<TfLauncher> tf;
   long long tf_min_batch = 0;        // smallest batch routed to the thread-per-frame kernel
   int tf_pairs_forced = 0;           // tuning knob LM_TF_PAIRS_PER_CLIP: 1 or 4 warp pairs per clip, 0 = by cost
+  int tf_slices_ok = 1;              // tuning knob LM_TF_SLICES=0: never spread a clip over several CTAs
   std::string tiled_name;            // the CTA-tiled kernel of this handle, as profilers print it
   int ctas_per_clip = 1;             // CTA-tiled kernels, steady state (tuning knob LM_CTAS_PER_CLIP)
   virtual ~lm_handle() {}
@@ -111,9 +112,15 @@ struct lm_handle {
 
 int TfLauncher::launch(const lm::KArgs& a, cudaStream_t st) {
   void* args[] = {(void*)&tab, (void*)&a};
-  const int grid = (int)std::min<long long>(n_sm, a.batch);   // clips spread over the SMs first (pair p of CTA c: clip p * grid + c)
-  cudaError_t e = cudaLaunchKernel(a.n_frames == 3000 ? kernel3000 : kernel, dim3(grid), dim3(lm::TfGeo::THREADS), args,
-                                   lm::TfGeo::SMEM_REQUEST, st);
+  const void* k = a.n_frames == 3000 ? kernel3000 : kernel;
+  const int slices = a.group > lm::TfGeo::PAIRS ? a.group / lm::TfGeo::PAIRS : 1;
+  cudaError_t e;
+  if (slices > 1) {     // a clip over several CTAs that wait for each other: all of them must be resident
+    e = cudaLaunchCooperativeKernel(k, dim3((unsigned)(a.batch * slices)), dim3(lm::TfGeo::THREADS), args, lm::TfGeo::SMEM_REQUEST, st);
+  } else {              // clips spread over the SMs first (pair p of CTA c: clip p * grid + c)
+    const int grid = (int)std::min<long long>(n_sm, a.batch);
+    e = cudaLaunchKernel(k, dim3(grid), dim3(lm::TfGeo::THREADS), args, lm::TfGeo::SMEM_REQUEST, st);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernel(logmel_tf_kernel)");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -238,12 +245,20 @@ int attach_tf(lm_handle* h, const lm_config* cfg, const float* window) {
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t->kernel, lm::TfGeo::THREADS, lm::TfGeo::SMEM_REQUEST));
   if (occ != 1) return fail(LM_ERR_NO_DEVICE, "thread-per-frame kernel: %d CTAs per SM (expected exactly 1: the CTA owns all of TMEM)", occ);
   h->tf = std::move(t);
-  // with a clip per CTA (tf_pairs_per_clip) one round of the kernel costs a quarter clip, ~150 us for 30 s of audio;
-  // the CTA-tiled kernel, which spreads a clip over many CTAs, is faster only while most SMs would have no clip
-  // (profiles/r02_dispatch_sweep.txt: 74 clips 120 vs 144 us, 148 clips 214 vs 156 us)
-  h->tf_min_batch = (long long)h->n_sm * 2 / 3;
+  // Batches too small for a clip per CTA (fewer clips than half the SMs) spread a clip over several CTAs
+  // (tf_pairs_per_clip); above that one round of the kernel costs a quarter clip.  The CTA-tiled kernel keeps the
+  // launches this one cannot take: other banks / log modes, unaligned clips, a handful of very short clips
+  // (profiles/r02_dispatch_sweep.txt: it loses at every batch size of 30 s clips).
+  h->tf_min_batch = (long long)h->n_sm / 2 + 1;
   if (const char* e = std::getenv("LM_TF_MIN_BATCH")) h->tf_min_batch = std::max(1, atoi(e));   // tuning knob
   if (const char* e = std::getenv("LM_TF_PAIRS_PER_CLIP")) h->tf_pairs_forced = atoi(e) == 4 ? 4 : atoi(e) == 1 ? 1 : 0;
+  if (const char* e = std::getenv("LM_TF_SLICES")) h->tf_slices_ok = atoi(e) != 0;
+  if (h->tf_min_batch > h->n_sm) h->tf_slices_ok = 0;      // LM_TF_MIN_BATCH=<huge>: the CTA-tiled kernel for everything
+  {
+    int coop_ok = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, cfg->device));
+    if (!coop_ok) h->tf_slices_ok = 0;
+  }
   return 0;
 }
 
@@ -254,7 +269,10 @@ int64_t frames_for(const lm_config& c, int64_t n_samples) {
 // the thread-per-frame kernel takes the launch when the handle has one, the clips are 16-byte
 // aligned (cp.async), the batch gives every warp pair a clip and a clip has at most kTfMaxTiles tiles
 bool use_tf(const lm_handle* h, int64_t batch, int64_t n_frames, bool aligned) {
-  return h->tf && aligned && batch >= h->tf_min_batch && (n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F <= lm::kTfMaxTiles;
+  const int64_t tiles = (n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F;
+  if (!h->tf || !aligned || tiles > lm::kTfMaxTiles) return false;
+  // enough clips for a quarter clip per warp pair -- or so few that a clip spreads over >= 2 CTAs (tf_pairs_per_clip)
+  return batch >= h->tf_min_batch || (h->tf_slices_ok && batch >= 1 && 2 * batch <= h->n_sm && tiles >= 2 * lm::TfGeo::PAIRS);
 }
 
 // Thread-per-frame kernel: a clip per warp pair, or a clip per CTA with a quarter of its tiles per pair?  In tile
@@ -266,6 +284,9 @@ int tf_pairs_per_clip(const lm_handle* h, int64_t batch, int tiles) {
   const int64_t P = lm::TfGeo::PAIRS, n = h->n_sm;
   const int64_t by_pair = ((batch + n * P - 1) / (n * P)) * tiles;
   const int64_t by_cta = ((batch + n - 1) / n) * ((tiles + P - 1) / P);
+  // small batches: a clip per several CTAs (at least two, at most one tile period per pair, kMaxGroup scratch slots)
+  const int64_t slices = std::min<int64_t>(std::min<int64_t>(n / std::max<int64_t>(batch, 1), kMaxGroup), (tiles + P - 1) / P);
+  if (slices >= 2 && h->tf_slices_ok) return (int)(P * slices);
   return by_cta * 102 < by_pair * 100 ? (int)P : 1;
 }
 
@@ -442,8 +463,9 @@ int forward_impl(lm_handle* h, const float* d_wave, const int16_t* d_pcm, int ch
   choose_grid(h, batch, a.tiles_per_clip, &a.group, &a.n_groups);
   a.vec_ok = (n_frames % 4 == 0) && (((uintptr_t)d_out & 15) == 0);
   // every clip starts 16-byte aligned (float32: TMA bulk copies / cp.async; PCM: 16-byte vector loads)
-  a.tma_ok = d_pcm ? ((((uintptr_t)d_pcm & 15) == 0) && ((clip_stride * channels) % 8 == 0))
-                   : ((((uintptr_t)d_wave & 15) == 0) && (clip_stride % 4 == 0));
+  // (a single clip has no stride to speak of)
+  a.tma_ok = d_pcm ? ((((uintptr_t)d_pcm & 15) == 0) && ((clip_stride * channels) % 8 == 0 || batch == 1))
+                   : ((((uintptr_t)d_wave & 15) == 0) && (clip_stride % 4 == 0 || batch == 1));
   const bool aligned = a.tma_ok != 0;
   a.timeline = nullptr;
 #ifdef LM_TIMELINE
@@ -459,6 +481,7 @@ int forward_impl(lm_handle* h, const float* d_wave, const int16_t* d_pcm, int ch
     a.tiles_per_clip = (int)((n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F);
     a.group = tf_pairs_per_clip(h, batch, a.tiles_per_clip);
     a.n_groups = 0;
+    if (a.group > lm::TfGeo::PAIRS) CUDA_TRY(cudaMemsetAsync(a.gcnt, 0, (size_t)batch * sizeof(int), st));
     rc = h->tf->launch(a, st);
   } else {
     if (d_pcm) a.tma_ok = 0;

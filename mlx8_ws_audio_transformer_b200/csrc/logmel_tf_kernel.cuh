@@ -374,13 +374,18 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
   // quarter-clip per SM where the first can waste a whole clip per pair, which is what mid-size batches need.  The
   // quarters are contiguous runs of tiles (measured 2.5 % faster than interleaving) unless per-clip lengths are given:
   // then every fourth tile, so that a short clip's few loud tiles spread over all four pairs (config 4: 1.02 -> 0.44 ms).
-  const bool coop = a.group == G::PAIRS;
-  const int gp = coop ? blockIdx.x : pair * gridDim.x + blockIdx.x;
-  const int gn = coop ? gridDim.x : gridDim.x * G::PAIRS;
-  const bool inter = coop && a.lengths != nullptr;
+  // Small batches (fewer clips than half the SMs) go one step further: a clip per `slices` CTAs (a.group = 4 * slices,
+  // grid = batch * slices, cooperative launch), every pair of them takes every (4 * slices)-th tile, and the CTAs
+  // agree on the clip maximum through the scratch buffer (gmax / gcnt, one release-acquire round per launch).
+  const bool coop = a.group >= G::PAIRS;
+  const int slices = a.group > G::PAIRS ? a.group / G::PAIRS : 1;
+  const int slice = slices > 1 ? (int)blockIdx.x % slices : 0;
+  const int gp = slices > 1 ? (int)blockIdx.x / slices : coop ? (int)blockIdx.x : pair * (int)gridDim.x + (int)blockIdx.x;
+  const int gn = slices > 1 ? a.batch : coop ? (int)gridDim.x : (int)gridDim.x * G::PAIRS;
+  const bool inter = coop && (a.lengths != nullptr || slices > 1);
   const int tq = (T + G::PAIRS - 1) / G::PAIRS;
-  const int t0 = !coop ? 0 : inter ? pair : min(pair * tq, T);       // this pair's tiles: t0, t0 + tstep, ... < t1
-  const int tstep = inter ? G::PAIRS : 1;
+  const int t0 = !coop ? 0 : inter ? slice * G::PAIRS + pair : min(pair * tq, T);   // this pair's tiles: t0, t0 + tstep, ... < t1
+  const int tstep = inter ? G::PAIRS * slices : 1;
   const int t1 = (!coop || inter) ? T : min((pair + 1) * tq, T);
   int par = 0;                                                       // clip parity: s_pmax is double-buffered
   for (int clip = gp; clip < a.batch; clip += gn, par ^= 1) {
@@ -655,11 +660,25 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
       __syncthreads();
 #pragma unroll
       for (int q = 0; q < G::PAIRS; ++q) cmax = fmaxf(cmax, fmaxf(s_pmax[par][q][0], s_pmax[par][q][1]));
+      if (slices > 1) {          // ... and the CTAs of the clip meet in global memory (all resident: cooperative launch)
+        if (threadIdx.x == 0) {
+          __stcg(a.gmax + (long long)clip * slices + slice, cmax);
+          __threadfence();
+          atomicAdd(a.gcnt + clip, 1);
+          long long spins = 0;
+          while (ld_acquire(a.gcnt + clip) < slices) {
+            __nanosleep(32);
+            if (++spins > (1ll << 24)) __trap();      // ~1 s: the launch was not cooperative / the counter not zeroed
+          }
+        }
+        __syncthreads();
+        for (int i = 0; i < slices; ++i) cmax = fmaxf(cmax, __ldcg(a.gmax + (long long)clip * slices + i));
+      }
     } else {
       pair_sync(pair);
       cmax = fmaxf(cmax, fmaxf(s_pmax[par][pair][0], s_pmax[par][pair][1]));
     }
-    if (role == 0 && lane == 0 && a.clip_max && (!coop || pair == 0)) a.clip_max[clip] = cmax;
+    if (role == 0 && lane == 0 && a.clip_max && (!coop || (pair == 0 && slice == 0))) a.clip_max[clip] = cmax;
     const float thr = fmaxf(cmax - 8.0f, silent_val);
     const float cval = vaffine(thr, 0.25f, 1.0f);
     const int mA = role == 0 ? 0 : MP::M0, mB = role == 0 ? MP::M0 : NM;            // this warp's filters

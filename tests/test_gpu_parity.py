@@ -193,7 +193,6 @@ def test_full_size_properties():
     fe = LogMelFrontend(400, 160, O.slaney_mel_filter_bank(201, 128), N.LOG10_CLAMP_WHISPER_NORM, 1e-10, True)
     B = 1184
     assert "logmel_tf_kernel<128, 3000>" in fe.kernel_name(B, 480000)
-    assert "logmel_ws_kernel" in fe.kernel_name(8, 480000)
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(B, 480000, generator=g, device="cuda") * 0.1
     x[17] = 0.0
@@ -217,12 +216,17 @@ def test_full_size_properties():
     # the dispatch threshold (2/3 clip per SM) and the clip-per-CTA work distribution mid-size batches take:
     # 1184 clips went a clip per warp pair, these go a clip per CTA -- same kernel, same bits
     n_sm = torch.cuda.get_device_properties(0).multi_processor_count
-    thr = 2 * n_sm // 3
-    assert "logmel_tf_kernel" in fe.kernel_name(thr, 480000) and "logmel_ws_kernel" in fe.kernel_name(thr - 1, 480000)
-    for nb in (thr, n_sm + 3, 4 * n_sm + 8):
+    # work distributions of the kernel: 1184 clips went a clip per warp pair; mid-size batches go a clip per CTA,
+    # small ones a clip over several CTAs (cooperative launch) -- same kernel, same bits
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    for nb in (1, 3, 32, n_sm // 2, n_sm // 2 + 1, n_sm + 3, 4 * n_sm + 8):
+        assert "logmel_tf_kernel" in fe.kernel_name(nb, 480000)
         assert torch.equal(fe.forward(x[5:5 + nb]), y[5:5 + nb]), nb
-    # a shard small enough for the CTA-tiled kernel agrees to float32 rounding, not bit for bit
-    assert (fe.forward(x[:40]) - y[:40]).abs().max() < 2e-6
+    assert "logmel_ws_kernel" in fe.kernel_name(8, 16000)           # a handful of 1 s clips: the CTA-tiled kernel
+    # the CTA-tiled kernel (here: forced by making the clips unaligned) agrees to float32 rounding, not bit for bit
+    xu = torch.empty(40 * 480001 + 1, device="cuda")[1:].view(40, 480001)[:, :480000]
+    xu.copy_(x[:40])
+    assert (fe.forward(xu) - y[:40]).abs().max() < 2e-6
 
 
 @pytest.mark.parametrize("kind", ["float32", "pcm16", "pcm16_stereo"])
