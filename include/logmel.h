@@ -73,8 +73,8 @@ typedef struct lm_config {
                                 0: emit 1 + n_samples/hop frames (torchaudio)                     */
   int32_t device;            /* CUDA device ordinal                                               */
   int32_t variant;           /* 0 = default: for the Whisper normalisation with the 80- / 128-filter
-                                Slaney bank, batches of >= 2/3 clip per SM run the thread-per-frame
-                                kernel (tensor memory as transpose scratch), everything else the
+                                Slaney bank, 16-byte-aligned clips of >= 8 tiles (2.5 s) run the thread-per-frame
+                                kernel (tensor memory as transpose scratch) at every batch size, everything else the
                                 CTA-tiled kernels (n_fft 400: warp-specialised CTA, two frames per lane);
                                 1 = CTA-tiled, one frame per lane (scalar FP32 path), 2 = CTA-tiled,
                                 two frames per lane, phase-synchronous CTA, 3 = thread-per-frame
