@@ -89,8 +89,8 @@ struct HostPipe {   // staging for lm_forward_host
 // every warp of the grid at least one clip.
 struct TfLauncher {
   lm::TfTables tab;
-  const void* kernel = nullptr;        // frames per clip read from the arguments
-  const void* kernel3000 = nullptr;    // 30 s clips: the store offsets are immediates
+  const void* kernel[2] = {nullptr, nullptr};        // frames per clip read from the arguments; [1]: clips split between pairs / CTAs
+  const void* kernel3000[2] = {nullptr, nullptr};    // 30 s clips: the store offsets are immediates
   int n_mels = 0, n_sm = 0;
   int launch(const lm::KArgs& a, cudaStream_t st);
 };
@@ -112,7 +112,8 @@ struct lm_handle {
 
 int TfLauncher::launch(const lm::KArgs& a, cudaStream_t st) {
   void* args[] = {(void*)&tab, (void*)&a};
-  const void* k = a.n_frames == 3000 ? kernel3000 : kernel;
+  const int split = a.group >= lm::TfGeo::PAIRS ? 1 : 0;
+  const void* k = a.n_frames == 3000 ? kernel3000[split] : kernel[split];
   const int slices = a.group > lm::TfGeo::PAIRS ? a.group / lm::TfGeo::PAIRS : 1;
   cudaError_t e;
   if (slices > 1) {     // a clip over several CTAs that wait for each other: all of them must be resident
@@ -235,14 +236,18 @@ int attach_tf(lm_handle* h, const lm_config* cfg, const float* window) {
   std::memset(&t->tab, 0, sizeof(t->tab));
   const bool ok = cfg->n_mels == 80 ? tf_fill<80>(t->tab, window, cfg->fbank) : tf_fill<128>(t->tab, window, cfg->fbank);
   if (!ok) return 0;
-  t->kernel = cfg->n_mels == 80 ? (const void*)lm::logmel_tf_kernel<80, 0> : (const void*)lm::logmel_tf_kernel<128, 0>;
-  t->kernel3000 = cfg->n_mels == 80 ? (const void*)lm::logmel_tf_kernel<80, 3000> : (const void*)lm::logmel_tf_kernel<128, 3000>;
+  t->kernel[0] = cfg->n_mels == 80 ? (const void*)lm::logmel_tf_kernel<80, 0, false> : (const void*)lm::logmel_tf_kernel<128, 0, false>;
+  t->kernel[1] = cfg->n_mels == 80 ? (const void*)lm::logmel_tf_kernel<80, 0, true> : (const void*)lm::logmel_tf_kernel<128, 0, true>;
+  t->kernel3000[0] = cfg->n_mels == 80 ? (const void*)lm::logmel_tf_kernel<80, 3000, false> : (const void*)lm::logmel_tf_kernel<128, 3000, false>;
+  t->kernel3000[1] = cfg->n_mels == 80 ? (const void*)lm::logmel_tf_kernel<80, 3000, true> : (const void*)lm::logmel_tf_kernel<128, 3000, true>;
   t->n_mels = cfg->n_mels;
   t->n_sm = h->n_sm;
-  CUDA_TRY(cudaFuncSetAttribute(t->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm::TfGeo::SMEM_REQUEST));
-  CUDA_TRY(cudaFuncSetAttribute(t->kernel3000, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm::TfGeo::SMEM_REQUEST));
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaFuncSetAttribute(t->kernel[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm::TfGeo::SMEM_REQUEST));
+    CUDA_TRY(cudaFuncSetAttribute(t->kernel3000[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm::TfGeo::SMEM_REQUEST));
+  }
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t->kernel, lm::TfGeo::THREADS, lm::TfGeo::SMEM_REQUEST));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, t->kernel[1], lm::TfGeo::THREADS, lm::TfGeo::SMEM_REQUEST));
   if (occ != 1) return fail(LM_ERR_NO_DEVICE, "thread-per-frame kernel: %d CTAs per SM (expected exactly 1: the CTA owns all of TMEM)", occ);
   h->tf = std::move(t);
   // Batches too small for a clip per CTA (fewer clips than half the SMs) spread a clip over several CTAs
@@ -400,9 +405,16 @@ int lm_kernel_info(const lm_handle* h, int32_t* n_sm, int32_t* ctas_per_sm, int3
 const char* lm_kernel_name(const lm_handle* h, int64_t batch, int64_t n_samples) {
   if (!h) return "";
   const int64_t n_frames = frames_for(h->cfg, n_samples);
-  if (use_tf(h, batch, n_frames, true))
-    return h->cfg.n_mels == 80 ? (n_frames == 3000 ? "lm::logmel_tf_kernel<80, 3000>" : "lm::logmel_tf_kernel<80, 0>")
-                               : (n_frames == 3000 ? "lm::logmel_tf_kernel<128, 3000>" : "lm::logmel_tf_kernel<128, 0>");
+  if (use_tf(h, batch, n_frames, true)) {
+    static const char* const names[2][2][2] = {
+        {{"lm::logmel_tf_kernel<80, 0, 0>", "lm::logmel_tf_kernel<80, 0, 1>"},
+         {"lm::logmel_tf_kernel<80, 3000, 0>", "lm::logmel_tf_kernel<80, 3000, 1>"}},
+        {{"lm::logmel_tf_kernel<128, 0, 0>", "lm::logmel_tf_kernel<128, 0, 1>"},
+         {"lm::logmel_tf_kernel<128, 3000, 0>", "lm::logmel_tf_kernel<128, 3000, 1>"}}};
+    const int tiles = (int)((n_frames + lm::TfGeo::F - 1) / lm::TfGeo::F);
+    const int split = tf_pairs_per_clip(h, batch, tiles) >= lm::TfGeo::PAIRS ? 1 : 0;   // third argument: clips are split
+    return names[h->cfg.n_mels == 80 ? 0 : 1][n_frames == 3000 ? 1 : 0][split];
+  }
   return h->tiled_name.c_str();
 }
 

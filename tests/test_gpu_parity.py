@@ -192,7 +192,7 @@ def test_full_size_properties():
     dispatch sends this batch (and its 592-clip shard below) to the thread-per-frame kernel."""
     fe = LogMelFrontend(400, 160, O.slaney_mel_filter_bank(201, 128), N.LOG10_CLAMP_WHISPER_NORM, 1e-10, True)
     B = 1184
-    assert "logmel_tf_kernel<128, 3000>" in fe.kernel_name(B, 480000)
+    assert "logmel_tf_kernel<128, 3000, 0>" in fe.kernel_name(B, 480000)         # a clip per warp pair
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(B, 480000, generator=g, device="cuda") * 0.1
     x[17] = 0.0
@@ -260,7 +260,7 @@ def test_guard_bands_thread_per_frame_kernel(fronts, kind):
     SENT = 1234.5
     big = torch.full((B + 2, 80, n_frames), SENT, device="cuda")
     cm = torch.full((B + 2,), SENT, device="cuda")
-    assert "logmel_tf_kernel<80, 0>" in fe.kernel_name(B, T)
+    assert "logmel_tf_kernel<80, 0, 1>" in fe.kernel_name(B, T)                    # run-time frame count, a clip per CTA
     got = fe.forward(x, lengths=lengths, out=big[1:B + 1], clip_max=cm[1:B + 1])
     torch.cuda.synchronize()
     assert torch.isfinite(got).all()

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "mlx8_ws_audio_transformer_b200", "csrc", "liblogmel_b200.so")
-KERNEL = "logmel_tf_kernelILi128ELi3000"
+KERNEL = "logmel_tf_kernelILi128ELi3000ELb0E"
 
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 res = subprocess.run(["cuobjdump", "-res-usage", so], capture_output=True, text=True).stdout
@@ -39,7 +39,7 @@ def n(prefix):
     return sum(v for k, v in full.items() if k.startswith(prefix))
 
 
-print(f"# SASS extract of the headline kernel (cuobjdump -sass {os.path.basename(so)}, function lm::logmel_tf_kernel<128, 3000>)")
+print(f"# SASS extract of the headline kernel (cuobjdump -sass {os.path.basename(so)}, function lm::logmel_tf_kernel<128, 3000, false>)")
 print(f"# {len(ops)} instructions ({len(ops) * 16 / 1024:.1f} KB); nvcc 12.9, -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo")
 print(f"# cuobjdump -res-usage: {usage}")
 print("#")
