@@ -671,7 +671,7 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
           long long spins = 0;
           while (ld_acquire(a.gcnt + clip) < slices) {
             __nanosleep(32);
-            if (++spins > (1ll << 24)) __trap();      // ~1 s: the launch was not cooperative / the counter not zeroed
+            if (++spins > (1ll << 24)) __trap();      // > 10 s: the launch was not cooperative / the counter not zeroed
           }
         }
         __syncthreads();

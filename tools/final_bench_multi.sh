@@ -14,4 +14,4 @@ import json; d=json.load(open('$O/$name.json')); print(d.get('value'), d.get('ms
 run cfg2_n8 8 --steps 10 --warmup 3 --no-cpu
 run cfg5_n8 8 --config 5 --steps 10 --warmup 3 --no-cpu
 run cfg2_n4 4 --steps 10 --warmup 3 --no-cpu
-run cfg2_n2 2 --steps 10 --warmup 3 --no-cpu
+[ -n "${LM_MULTI_SHORT:-}" ] || run cfg2_n2 2 --steps 10 --warmup 3 --no-cpu
