@@ -574,10 +574,6 @@ logmel_tf_kernel(const __grid_constant__ TfTables ctab, const KArgs a) {
       if (pcm_staged) {          // (16-bit PCM input only) the raw frames this warp copied -> its rows of the float tile,
         __syncwarp();            //  which has been dead since the stage-1 barrier of the previous tile
         pcm_convert();
-#ifdef LM_DBG_CONVERT2
-        __syncwarp();
-        pcm_convert();
-#endif
       }
       pair_sync(pair);           // the tile is complete; the partner has finished reading P of the previous tile
       // Lanes past the clip's last frame (only in its last tile) redo the last valid frame: same
